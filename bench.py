@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- calibration / fake-quant throughput of the PPQ quantization-simulation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): ResNet-50 RuntimeCalibrationPass, minmax + KL-histogram, synthetic 3x224x224 samples,
+calibration batch B = 32 (the reference's ImageNet calibration batch: ppq/samples/QuantZoo/QuantZoo_Imagenet.py:21), K = 16 steps
+= 512 samples per GPU.  One "step" = one calibration batch through the hot path, both phases:
+    phase 1   per-channel INT8 fake-quant of the 54 Conv/Gemm weights (the executor re-quantises weights every forward:
+              executor/torch.py:516-518) + fused min/max over the 106 observed activation tensors of the forward
+    phase 2   the same weight fake-quant + 4096-bin histogram over the same activation tensors
+and the timed region ends with the two exchange steps (all-reduce of {min,max}, all-reduce of the histogram arena) and the
+on-device KL scale search.  Conv/Gemm forward execution itself is outside the path (stays in torch/cuDNN), so
+`value` replays the activation tensor set of the network (shapes traced from torchvision resnet50 after BN fusion; synthetic
+randn / relu(randn) values) resident in HBM; `e2e` runs the real thing -- images from pinned host memory, torch forward of the
+network with our hooks, scales read back -- through ppq_b200's public API.
+
+Prints ONE JSON line (see the task contract): metric/value (imgs/s, whole job), roofline of the dominant kernel,
+cpu_baseline (the reference's USING_CUDA_KERNEL=False CPU path restated in oracle/ with torch CPU ops, timed on this host), clocks,
+e2e, gpu_launches, plus `fakequant` (LinearQuant elems/s and HBM fraction over 1x3x224x224 ... 1x2048x64x64).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'calibration_imgs_per_s'
+UNIT = 'imgs/s'
+BINS = 4096
+
+
+# ------------------------------------------------------------------------------------------------ workload definition
+def resnet50_tensor_table():
+    """Per-image shapes of the observed activations (model input + output of every Conv / ReLU call site / pool / fc, BatchNorm
+    folded into the convs as PPQ does at load: core/common.py:41) and the shapes of the Conv/Gemm weights.  Traced on the meta
+    device; falls back to the recorded table if torchvision is unavailable."""
+    try:
+        import torchvision
+        m = torchvision.models.resnet50(weights=None).eval().to('meta')
+        acts, weights = [(3, 224, 224)], []
+        hooks = []
+        for mod in m.modules():
+            if isinstance(mod, (torch.nn.Conv2d, torch.nn.ReLU, torch.nn.MaxPool2d, torch.nn.AdaptiveAvgPool2d, torch.nn.Linear)):
+                hooks.append(mod.register_forward_hook(lambda _m, _i, o: acts.append(tuple(o.shape[1:]))))
+            if isinstance(mod, (torch.nn.Conv2d, torch.nn.Linear)):
+                weights.append(tuple(mod.weight.shape))
+        with torch.no_grad():
+            m(torch.empty(1, 3, 224, 224, device='meta'))
+        for h in hooks: h.remove()
+        return acts, weights
+    except Exception:
+        acts = [(3, 224, 224), (64, 112, 112), (64, 112, 112), (64, 56, 56)]
+        weights = [(64, 3, 7, 7)]
+        cfg = [(64, 256, 56, 3), (128, 512, 28, 4), (256, 1024, 14, 6), (512, 2048, 7, 3)]
+        cin = 64
+        for mid, out, hw, blocks in cfg:
+            for b in range(blocks):
+                first = b == 0
+                hw_in = hw * 2 if (first and mid != 64) else hw
+                acts += [(mid, hw_in, hw_in), (mid, hw_in, hw_in), (mid, hw, hw), (mid, hw, hw), (out, hw, hw)]
+                weights += [(mid, cin, 1, 1), (mid, mid, 3, 3), (out, mid, 1, 1)]
+                if first:
+                    acts.append((out, hw, hw)); weights.append((out, cin, 1, 1))
+                acts.append((out, hw, hw))
+                cin = out
+        acts += [(2048, 1, 1), (1000,)]
+        weights.append((1000, 2048))
+        return acts, weights
+
+
+def numel(shape):
+    n = 1
+    for d in shape: n *= d
+    return n
+
+
+class Workload:
+    """R rotating sets of synthetic activation tensors for one calibration batch + the network's weights, resident in HBM."""
+
+    def __init__(self, device, batch, rotate, seed=0):
+        self.acts, self.weights = resnet50_tensor_table()
+        self.batch, self.device = batch, device
+        g = torch.Generator(device=device).manual_seed(seed)
+        self.sets = []
+        for r in range(rotate):
+            ts = []
+            for i, shp in enumerate(self.acts):
+                t = torch.randn((batch,) + shp, device=device, generator=g)
+                if i % 2 == 1: t.relu_()                                  # post-ReLU tensors: half of the mass in bin 0
+                ts.append(t)
+            self.sets.append(ts)
+        self.w = [torch.randn(shp, device=device, generator=g) * 0.05 for shp in self.weights]
+        self.w_scale = [(w.abs().amax(dim=tuple(range(1, w.dim()))) / 127).clamp_min(1e-8).contiguous() for w in self.w]
+        self.w_offset = [torch.zeros_like(s) for s in self.w_scale]
+        self.act_elems = sum(numel(s) for s in self.acts) * batch
+        self.w_elems = sum(numel(s) for s in self.weights)
+
+    def bytes_per_step(self):
+        # algorithmic HBM bytes: 4 B/elem per collector pass (2 passes) + 8 B/elem per weight fake-quant (2 forwards)
+        return 2 * 4 * self.act_elems + 2 * 8 * self.w_elems
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler(threading.Thread):
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out: self.samples.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples: return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                'reasons': reasons, 'samples': len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, world, local_rank):
+    from ppq_b200.calibration import ArenaCalibrator
+    from ppq_b200.ffi import extension
+    ext = extension()
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    wl = Workload(device, args.batch, args.rotate, seed=1234 + rank)
+    T = len(wl.acts)
+    cal = ArenaCalibrator(T, device, bins=BINS, num_of_bits=8, method='kl')
+    stream = torch.cuda.current_stream()
+    hist_events, mm_events, launches = [], [], [0]
+
+    def weights_pass():
+        for w, s, o in zip(wl.w, wl.w_scale, wl.w_offset):
+            ext.QuantizeTensor_LC(w, s, o, -128, 127, 0, 0)
+        launches[0] += len(wl.w)
+
+    def calibrate(steps, timed):
+        cal.reset()
+        for k in range(steps):                                  # phase 1
+            weights_pass()
+            if timed: e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record(stream)
+            cal.observe(wl.sets[k % args.rotate])
+            if timed: e1.record(stream); mm_events.append((e0, e1))
+        cal.end_phase()
+        for k in range(steps):                                  # phase 2
+            weights_pass()
+            if timed: e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record(stream)
+            cal.observe(wl.sets[k % args.rotate])
+            if timed: e1.record(stream); hist_events.append((e0, e1))
+        cal.end_phase()
+        return cal.scale
+
+    def barrier():
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+
+    calibrate(max(args.warmup, 1), False)                       # W untimed warm-up steps (both phases)
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    cal.launches = 0; launches[0] = 0
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    scales = calibrate(args.steps, True)
+    t1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], device=device); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
+    assert torch.isfinite(scales).all() and (scales > 0).all()
+
+    # ---- roofline of the dominant kernel (multi-tensor histogram; 4 B/element) from the events of the timed region
+    peak, peak_src = measured_peaks()
+    h_ms = sum(a.elapsed_time(b) for a, b in hist_events) / len(hist_events)
+    m_ms = sum(a.elapsed_time(b) for a, b in mm_events) / len(mm_events)
+    hist_gbs = 4.0 * wl.act_elems / (h_ms * 1e-3) / 1e9
+    mm_gbs = 4.0 * wl.act_elems / (m_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'multi_histogram_t_kernel', 'achieved': round(hist_gbs, 1), 'peak': peak, 'unit': 'GB/s',
+                'frac': round(hist_gbs / peak, 4), 'traffic': None, 'peak_source': peak_src, 'ms_per_launch': round(h_ms, 4),
+                'algorithmic_bytes_per_launch': 4 * wl.act_elems,
+                'other_kernels': {'multi_minmax_t_kernel': {'achieved': round(mm_gbs, 1), 'frac': round(mm_gbs / peak, 4), 'ms_per_launch': round(m_ms, 4)}}}
+    result = {
+        'metric': METRIC, 'value': round(world * args.steps * args.batch / (ms * 1e-3), 1), 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms / args.steps, 4), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'ResNet-50 RuntimeCalibrationPass (minmax + KL 4096-bin histogram), 3x224x224 samples', 'batch': args.batch,
+                   'samples_per_gpu': args.steps * args.batch, 'observed_tensors': T, 'observed_elems_per_image': wl.act_elems // args.batch,
+                   'weight_tensors': len(wl.w), 'weight_elems': wl.w_elems, 'parallelism': f'dp{world} (sample-sharded, 2 all-reduces)',
+                   'l2_policy': f'inputs larger than L2: {args.rotate} rotating activation sets of {4 * wl.act_elems / 1e9:.2f} GB each'},
+        'roofline': roofline,
+        'gpu_launches': cal.launches + launches[0],
+        'clocks': sampler.summary(),
+        'algorithmic_gbs': round(wl.bytes_per_step() / (ms / args.steps * 1e-3) / 1e9, 1),
+    }
+    if rank == 0:
+        result['fakequant'] = fakequant_sweep(ext, device, peak)
+        result['e2e'] = run_e2e(args, device, world) if not args.no_e2e else None
+        result['cpu_baseline'] = cpu_baseline(args, sample_steps=2)
+    elif not args.no_e2e:
+        run_e2e(args, device, world)
+    return result
+
+
+def fakequant_sweep(ext, device, peak):
+    """LinearQuant_T INT8 over the north-star shape range.  Big shapes rotate over > L2 worth of distinct buffers; the small ones
+    are launch-latency bound and L2 resident by nature -- reported as latency."""
+    out = []
+    s, o = torch.tensor([0.05], device=device), torch.tensor([0.0], device=device)
+    for shape in ((1, 3, 224, 224), (1, 512, 28, 28), (1, 256, 56, 56), (1, 1024, 14, 14), (1, 2048, 64, 64), (32, 512, 768), (32, 12, 512, 512)):
+        n = numel(shape)
+        nbuf = max(2, min(64, int(1.5e9 // (8 * n)) + 1))
+        xs = [torch.randn(shape, device=device) for _ in range(nbuf)]
+        ys = [torch.empty_like(x) for x in xs]
+        import ctypes
+        lib = ctypes.CDLL(os.path.join(ROOT, 'ppq_b200', '_lib', 'libppq_b200.so'))
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def launch(i):
+            lib.ppq_b200_linear_quant_t(ctypes.c_void_p(xs[i].data_ptr()), ctypes.c_void_p(ys[i].data_ptr()), ctypes.c_int64(n),
+                                        ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(o.data_ptr()), -128, 127, 0, st)
+        for i in range(nbuf): launch(i)
+        reps = max(nbuf, 40)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); a.record()
+        for i in range(reps): launch(i % nbuf)
+        b.record(); torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / reps
+        gbs = 8.0 * n / (us * 1e-6) / 1e9
+        out.append({'shape': 'x'.join(map(str, shape)), 'elems': n, 'us_per_call': round(us, 2), 'gelems_per_s': round(n / us / 1e3, 1),
+                    'gbs': round(gbs, 1), 'frac_of_hbm_peak': round(gbs / peak, 4), 'distinct_buffers': nbuf})
+        del xs, ys
+    return out
+
+
+def run_e2e(args, device, world):
+    try:
+        from ppq_b200.executor import e2e_calibration_benchmark
+    except Exception as e:                                               # executor lands after the kernels; never silently fake a number
+        return {'value': None, 'unit': UNIT, 'unavailable': f'{type(e).__name__}: {e}'}
+    return e2e_calibration_benchmark(batch=args.batch, steps=max(args.steps, 8), warmup=1, device=device, world=world)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port of the reference CPU path)
+def cpu_steps(batch, steps, seed=0):
+    """The reference's USING_CUDA_KERNEL=False path on the host cores, restated in oracle/ with torch CPU ops
+    (qfunction/linear.py:73-81, observer/range.py:91-92, :183, :190-282).  Returns seconds for `steps` calibration batches (both phases)."""
+    import oracle as ora
+    torch.set_num_threads(os.cpu_count() or 1)
+    acts, weights = resnet50_tensor_table()
+    g = torch.Generator().manual_seed(seed)
+    ts = []
+    for i, shp in enumerate(acts):
+        t = torch.randn((batch,) + shp, generator=g)
+        if i % 2 == 1: t.relu_()
+        ts.append(t)
+    ws = [torch.randn(shp, generator=g) * 0.05 for shp in weights]
+    wscale = [(w.abs().amax(dim=tuple(range(1, w.dim()))) / 127).clamp_min(1e-8) for w in ws]
+    woff = [torch.zeros_like(s) for s in wscale]
+    t0 = time.perf_counter()
+    mins = [float('inf')] * len(ts); maxs = [float('-inf')] * len(ts)
+    for _ in range(steps):
+        for w, s, o in zip(ws, wscale, woff): ora.torch_cpu_linear_quant_c(w, s, o, 0, -128, 127)
+        for i, t in enumerate(ts):
+            lo, hi = ora.torch_cpu_minmax(t)
+            mins[i] = min(mins[i], lo.item()); maxs[i] = max(maxs[i], hi.item())
+    hs = [max(abs(a), abs(b)) / BINS for a, b in zip(mins, maxs)]
+    hists = [torch.zeros(BINS, dtype=torch.int32) for _ in ts]
+    for _ in range(steps):
+        for w, s, o in zip(ws, wscale, woff): ora.torch_cpu_linear_quant_c(w, s, o, 0, -128, 127)
+        for i, t in enumerate(ts): hists[i] += ora.torch_cpu_hist_sym(t, hs[i], BINS)
+    for h, s in zip(hists, hs): ora.kl_search(h, s, 8)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(args, sample_steps):
+    secs = cpu_steps(args.batch, sample_steps)
+    return {'value': round(sample_steps * args.batch / secs, 2), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{sample_steps} calibration batches of {args.batch} images (both phases + KL search), torch CPU ops, '
+                      f'oracle/ restatement of the reference USING_CUDA_KERNEL=False path; {secs:.1f} s'}
+
+
+def run_reference(args, rank, world):
+    if rank != 0: return None
+    steps = min(args.steps, 4)
+    for _ in range(min(args.warmup, 1)): cpu_steps(args.batch, 1)
+    secs = cpu_steps(args.batch, steps)
+    v = round(steps * args.batch / secs, 2)
+    acts, weights = resnet50_tensor_table()
+    return {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': round(secs / steps * 1e3, 2), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'ResNet-50 RuntimeCalibrationPass (minmax + KL 4096-bin histogram), 3x224x224 samples', 'batch': args.batch,
+                       'observed_tensors': len(acts), 'weight_tensors': len(weights), 'parallelism': 'host cores, 1 process'},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                             'sample': f'each step = one calibration batch of {args.batch} images; {steps} of the {args.steps} requested steps timed '
+                                       f'(bounded sample), torch CPU ops on {torch.get_num_threads()} threads'},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=16)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=32)
+    ap.add_argument('--rotate', type=int, default=4, help='distinct activation sets cycled through (each > L2)')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        res = run_reference(args, rank, world)
+        if res is not None: print(json.dumps(res), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm')
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    res = run_ours(args, rank, world, local_rank)
+    if rank == 0: print(json.dumps(res), flush=True)
+    if world > 1: dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,238 @@
+"""Calibration drivers: the mirror of RuntimeCalibrationPass (/root/reference/ppq/quantization/optim/calibration.py:19-213)
+re-designed around a device-resident statistics arena and sample-sharded data parallelism.
+
+  ArenaCalibrator          the B200-native two-phase calibrator.  All T observed tensors of one forward are collected by ONE
+                           multi-tensor launch per phase (Multi_MinMax_T / Multi_Histogram_T) into one contiguous arena:
+                               minmax [T,2] fp32,  hist_scale [T] fp32,  hist [T,bins] int32.
+                           Rank r of R processes sees samples r, r+R, ...; the whole multi-GPU exchange is
+                               phase 1:  ONE all-reduce(MAX) over the packed {-min, max} buffer      (2*T floats)
+                               phase 2:  ONE all-reduce(SUM) over the int32 histogram arena           (T*bins ints)
+                           both exact and order-independent, so R ranks reproduce the 1-rank result bit for bit.
+                           Scales come from the on-device searches (MinMax_To_Scale_Offset, KL_Search): no per-tensor host sync.
+  RuntimeCalibrationPass   the reference's hook-driven flow (build observers -> phase 1 over the dataloader -> render -> drop the
+                           one-phase observers -> phase 2 -> render) for any executor with forward(inputs, hooks=...), using the
+                           observers of ppq_b200.observer; `calib_steps` keeps the reference's 8..512 contract.
+"""
+from math import ceil
+from typing import Callable, Dict, Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from .core import OBSERVER_KL_HIST_BINS, OBSERVER_MIN_SCALE, QuantizationProperty, QuantizationStates
+
+
+# ---- the two exchange steps (pure torch.distributed; CPU/gloo-testable) --------------------------------------------------------
+def pack_minmax_for_max_reduce(minmax: torch.Tensor) -> torch.Tensor:
+    """[T,2] {min,max} -> [T,2] {-min, max}: a single MAX all-reduce then reduces both ends exactly."""
+    packed = minmax.clone()
+    packed[:, 0].neg_()
+    return packed
+
+
+def unpack_minmax_after_max_reduce(packed: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    out.copy_(packed)
+    out[:, 0].neg_()
+    return out
+
+
+def allreduce_minmax(minmax: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        packed = pack_minmax_for_max_reduce(minmax)
+        dist.all_reduce(packed, op=dist.ReduceOp.MAX, group=group)
+        unpack_minmax_after_max_reduce(packed, minmax)
+    return minmax
+
+
+def allreduce_hist(hist: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist
+
+
+def shard_indices(num_samples: int, rank: int, world_size: int) -> range:
+    """Sample partition of SURVEY §8e: rank r takes samples r, r + R, r + 2R, ..."""
+    return range(rank, num_samples, world_size)
+
+
+# ---- arena calibrator -------------------------------------------------------------------------------------------------------------
+class ArenaCalibrator:
+    def __init__(self, num_tensors: int, device, bins: int = OBSERVER_KL_HIST_BINS, num_of_bits: int = 8,
+                 quant_min: int = -128, quant_max: int = 127, power_of_2: bool = False, min_scale: float = OBSERVER_MIN_SCALE,
+                 method: str = 'kl', group=None):
+        from .ffi import extension
+        assert method in ('kl', 'minmax')
+        self.ext = extension()
+        self.T, self.bins, self.device, self.group = num_tensors, bins, torch.device(device), group
+        self.num_of_bits, self.quant_min, self.quant_max = num_of_bits, quant_min, quant_max
+        self.power_of_2, self.min_scale, self.method = power_of_2, min_scale, method
+        self.minmax = torch.empty(num_tensors, 2, dtype=torch.float32, device=self.device)
+        self.hist = torch.zeros(num_tensors, bins, dtype=torch.int32, device=self.device)
+        self.hist_scale = torch.zeros(num_tensors, dtype=torch.float32, device=self.device)
+        self.scale = self.offset = self.best_bin_range = None
+        self._desc_cache: Dict[tuple, tuple] = {}
+        self.launches = 0
+        self.reset()
+
+    def reset(self):
+        self.minmax[:, 0] = float('inf'); self.minmax[:, 1] = float('-inf')
+        self.hist.zero_()
+        self.phase = 1
+
+    def _descs(self, tensors: Sequence[torch.Tensor]):
+        key = tuple((t.data_ptr(), t.numel()) for t in tensors)
+        hit = self._desc_cache.get(key)
+        if hit is None:
+            assert len(tensors) == self.T, f'expected {self.T} tensors per forward, got {len(tensors)}'
+            for t in tensors:
+                if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                    raise RuntimeError('ArenaCalibrator needs contiguous fp32 CUDA tensors')
+            host = torch.tensor([[p, n, i] for i, (p, n) in enumerate(key)], dtype=torch.int64).pin_memory()
+            hit = (host.to(self.device, non_blocking=True), max(n for _, n in key))
+            if len(self._desc_cache) < 64: self._desc_cache[key] = hit
+        return hit
+
+    @torch.no_grad()
+    def observe(self, tensors: Sequence[torch.Tensor]):
+        descs, max_n = self._descs(tensors)
+        if self.phase == 1:
+            self.ext.Multi_MinMax_T(descs, max_n, self.minmax)
+        else:
+            self.ext.Multi_Histogram_T(descs, max_n, self.hist_scale, True, self.hist, self.bins)
+        self.launches += 1
+
+    @torch.no_grad()
+    def end_phase(self):
+        """Exchange + render of the finished phase.  Returns True when calibration is complete."""
+        if self.phase == 1:
+            allreduce_minmax(self.minmax, self.group)
+            if self.method == 'minmax':
+                self.scale, self.offset = self.ext.MinMax_To_Scale_Offset(self.minmax.view(-1), self.minmax.view(-1)[1:], 2, self.quant_min,
+                                                                          self.quant_max, True, self.power_of_2, self.min_scale)
+                self.launches += 1
+                return True
+            self.hist_scale = self.ext.Hist_Scale_From_MinMax(self.minmax, True, self.bins)
+            self.launches += 1
+            self.phase = 2
+            return False
+        allreduce_hist(self.hist, self.group)
+        self.scale, self.best_bin_range = self.ext.KL_Search(self.hist, self.bins, self.hist_scale, self.minmax, self.num_of_bits,
+                                                             self.power_of_2, self.min_scale)
+        self.offset = torch.zeros_like(self.scale)
+        self.launches += 1
+        return True
+
+
+# ---- hook-driven pass (reference flow) --------------------------------------------------------------------------------------------
+class CalibrationHook:
+    """observer/__init__.py:40-72: calls observe() on the fp32 inputs / outputs of one quantable operation."""
+
+    def __init__(self, operation, observer_table: dict):
+        self._operation, self._observer_table = operation, observer_table
+
+    def pre_forward_hook(self, inputs: list, quant_inputs: list, quant_configs: list) -> list:
+        for input_var, quant_config in zip(inputs, quant_configs):
+            ob = self._observer_table.get(id(quant_config))
+            if ob is not None: ob.observe(input_var)
+        return quant_inputs
+
+    def post_forward_hook(self, outputs: list, quant_outputs: list, quant_configs: list) -> list:
+        for output_var, quant_config in zip(outputs, quant_configs):
+            ob = self._observer_table.get(id(quant_config))
+            if ob is not None: ob.observe(output_var)
+        return quant_outputs
+
+    def render_quantization_config(self):
+        for ob in self._observer_table.values():
+            ob.render_quantization_config()
+
+
+class OperationObserver:
+    """observer/__init__.py:75-124."""
+
+    def __init__(self, operation, monitor_parameter: bool = True, monitor_outputs: bool = True, monitor_inputs: bool = True):
+        from .observer import TensorObserverFactroy
+        table = {}
+        for var, config, is_param in operation.input_configs():
+            if config.state == QuantizationStates.INITIAL:
+                if is_param and monitor_parameter: table[id(config)] = TensorObserverFactroy.build_observer(var, config)
+                elif not is_param and monitor_inputs: table[id(config)] = TensorObserverFactroy.build_observer(var, config)
+        if monitor_outputs:
+            for var, config in operation.output_configs():
+                if config.state == QuantizationStates.INITIAL:
+                    table[id(config)] = TensorObserverFactroy.build_observer(var, config)
+        self._operation, self._hook = operation, CalibrationHook(operation, table)
+
+    @property
+    def hook(self) -> CalibrationHook:
+        return self._hook
+
+    def render_quantization_config(self):
+        self._hook.render_quantization_config()
+
+
+class RuntimeCalibrationPass:
+    """calibration.py:19-213, including the 8 <= calib_steps <= 512 contract (:136-142).  With torch.distributed initialised the
+    dataloader is sharded by sample (rank r keeps batches r, r+R, ...) and the observers' arena is all-reduced at the end of each phase."""
+
+    def __init__(self, method: str = None, override: bool = False, calib_steps: int = 32, group=None):
+        self._method, self._override, self._calib_steps, self._group = method, override, calib_steps, group
+        self._observers, self._collate_fn = {}, None
+
+    def calibrate(self, dataloader: Iterable, executor, hooks: dict):
+        world = dist.get_world_size(self._group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(self._group) if world > 1 else 0
+        calib_step = 0
+        for _ in range(ceil(self._calib_steps / len(dataloader))):
+            for idx, data in enumerate(dataloader):
+                if world > 1 and idx % world != rank:
+                    calib_step += 1
+                    if calib_step >= self._calib_steps: break
+                    continue
+                if self._collate_fn is not None: data = self._collate_fn(data)
+                executor.forward(inputs=data, hooks=hooks)
+                calib_step += 1
+                if calib_step >= self._calib_steps: break
+            if calib_step >= self._calib_steps: break
+
+    def _reduce(self, phase: int):
+        from .observer import TorchHistObserver, TorchMinMaxObserver
+        obs = [ob for o in self._observers.values() for ob in o.hook._observer_table.values()]
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(self._group) > 1): return
+        if phase == 1:
+            mm = [ob for ob in obs if isinstance(ob, TorchMinMaxObserver) and ob._slot is not None and ob._slot.cmins is None]
+            if mm:
+                buf = torch.stack([ob._slot.minmax for ob in mm])
+                allreduce_minmax(buf, self._group)
+                for ob, row in zip(mm, buf): ob._slot.minmax.copy_(row)
+        else:
+            hs = [ob for ob in obs if isinstance(ob, TorchHistObserver) and ob._slot is not None]
+            if hs:
+                buf = torch.stack([ob._slot.hist for ob in hs])
+                allreduce_hist(buf, self._group)
+                for ob, row in zip(hs, buf): ob._slot.hist.copy_(row)
+
+    def optimize(self, graph, dataloader: Iterable, executor, calib_steps: int = 32, collate_fn: Callable = None, **kwargs) -> None:
+        from .observer import TorchHistObserver, TorchMSEObserver
+        if collate_fn is not None: self._collate_fn = collate_fn
+        if calib_steps is not None: self._calib_steps = calib_steps
+        assert calib_steps >= 8, 'Insufficient Calibration Detected (at least 8 calibration steps).'
+        assert calib_steps <= 512, 'Calibration steps is too large, ppq can quantize your network within 8-512 calibration steps.'
+        hooks = {}
+        for op_name, operation in graph.quantable_operations():
+            for _, config, is_param in operation.input_configs():
+                if not is_param and self._method is not None: config.observer_algorithm = self._method
+            for _, config in operation.output_configs():
+                if self._method is not None: config.observer_algorithm = self._method
+            observer = OperationObserver(operation=operation, monitor_parameter=False)
+            self._observers[op_name], hooks[op_name] = observer, observer.hook
+        self.calibrate(dataloader, executor, hooks)
+        self._reduce(1)
+        for observer in self._observers.values(): observer.render_quantization_config()
+        for op_name in [n for n, o in self._observers.items()
+                        if all(type(v) not in {TorchHistObserver, TorchMSEObserver} for v in o.hook._observer_table.values())]:
+            self._observers.pop(op_name); hooks.pop(op_name)
+        if len(hooks) > 0:
+            self.calibrate(dataloader, executor, hooks)
+            self._reduce(2)
+            for observer in self._observers.values(): observer.render_quantization_config()

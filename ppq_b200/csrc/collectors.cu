@@ -1,0 +1,453 @@
+// collectors.cu -- sm_100a calibration collectors behind the C ABI of include/ppq_b200.h.
+//
+//   ppq_b200_minmax_t / _c          fused single-pass min+max; replaces the two torch reductions of
+//                                   TorchMinMaxObserver.observe (/root/reference/ppq/quantization/observer/range.py:85-100)
+//   ppq_b200_histogram_t            replaces Histogram_T            (ppq/csrc/cuda/sort.cu:75-111)
+//   ppq_b200_histogram_asym_t       replaces Histogram_Asymmetric_T (sort.cu:113-165)
+//   ppq_b200_histogram_c            replaces Histogram_C            (sort.cu:167-218)
+//   ppq_b200_multi_*                one launch over a table of tensors (the calibration arena path)
+//
+// All of them read each element exactly once (4 B/element algorithmic traffic) with 128-bit streaming loads, four per
+// thread in flight.  Histograms are privatised per CTA in shared memory (bins x int32, 16 KB for the KL observer's 4096
+// bins), the post-ReLU hot spot (bin 0) is counted with a warp ballot instead of 32-way same-address atomics, and only
+// non-empty bins are flushed to the caller's global histogram with red.global.add.
+#include "common.cuh"
+#include "../../include/ppq_b200.h"
+#include "variants.h"
+
+namespace ppqb {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+__device__ __forceinline__ float min_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
+// NaN-propagating (min, max) of a thread's values -> warp -> CTA; result valid in thread 0.
+struct MinMax {
+    float lo, hi;
+    __device__ __forceinline__ MinMax() { lo = __int_as_float(0x7F800000); hi = __int_as_float(0xFF800000); }
+    __device__ __forceinline__ void add(float v) { lo = min_nan(lo, v); hi = max_nan(hi, v); }
+    __device__ __forceinline__ void add4(const float4 &v) { add(v.x); add(v.y); add(v.z); add(v.w); }
+    __device__ __forceinline__ void warp_reduce() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min_nan(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max_nan(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+    }
+    // publish into accumulating global slots (see common.cuh: raw-bit float atomics, NaN poisons both slots)
+    __device__ __forceinline__ void publish(float *gmin, float *gmax) const {
+        if (lo != lo || hi != hi) {
+            atomic_min_float(gmin, __uint_as_float(0xFFC00000u));
+            atomic_max_float(gmax, __uint_as_float(0x7FC00000u));
+        } else {
+            atomic_min_float(gmin, lo);
+            atomic_max_float(gmax, hi);
+        }
+    }
+};
+
+__device__ __forceinline__ void block_reduce_publish(MinMax mm, float *gmin, float *gmax) {
+    __shared__ float s_lo[kThreads / 32], s_hi[kThreads / 32];
+    mm.warp_reduce();
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_lo[w] = mm.lo; s_hi[w] = mm.hi; }
+    __syncthreads();
+    if (w == 0) {
+        MinMax t;
+        if (l < kThreads / 32) { t.lo = s_lo[l]; t.hi = s_hi[l]; }
+        t.warp_reduce();
+        if (l == 0) t.publish(gmin, gmax);
+    }
+    __syncthreads();
+}
+
+// Streams elements [0, n) of x through `f(float)`; float4 path when the base is 16-byte aligned.
+// `first`/`stride` are in units of threads over the whole cooperating group (a grid or a sub-grid).
+template <class F>
+__device__ __forceinline__ void stream_elements(const float *__restrict__ x, int64_t n, int64_t first, int64_t stride, F &&f) {
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+        const int64_t n4 = n >> 2;
+        const float4 *x4 = reinterpret_cast<const float4 *>(x);
+        int64_t i = first;
+        for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
+            float4 v[kUnroll];
+#pragma unroll
+            for (int j = 0; j < kUnroll; j++) v[j] = ld_stream4(x4 + i + j * stride);
+#pragma unroll
+            for (int j = 0; j < kUnroll; j++) { f(v[j].x); f(v[j].y); f(v[j].z); f(v[j].w); }
+        }
+        for (; i < n4; i += stride) { const float4 v = ld_stream4(x4 + i); f(v.x); f(v.y); f(v.z); f(v.w); }
+        const int64_t t = (n4 << 2) + first;
+        if (t < n) f(x[t]);
+    } else {
+        for (int64_t i = first; i < n; i += stride) f(ld_stream1(x + i));
+    }
+}
+
+// ---- min / max ------------------------------------------------------------------------------------------------------
+__global__ void minmax_init_kernel(float *mins, float *maxs, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        if (mins) mins[i] = __int_as_float(0x7F800000);
+        if (maxs) maxs[i] = __int_as_float(0xFF800000);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+minmax_t_kernel(const float *__restrict__ x, int64_t n, float *__restrict__ minmax) {
+    MinMax mm;
+    stream_elements(x, n, (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads,
+                    [&](float v) { mm.add(v); });
+    block_reduce_publish(mm, minmax, minmax + 1);
+}
+
+// One tensor per descriptor, work item = (tensor, chunk of `chunk` elements); blockIdx.x walks the items.
+__global__ void __launch_bounds__(kThreads)
+multi_minmax_t_kernel(const ppq_b200_tensor_desc *__restrict__ descs, int count, int64_t chunk, int chunks_per_tensor,
+                      float *__restrict__ arena) {
+    const int64_t items = (int64_t)count * chunks_per_tensor;
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int t = (int)(item / chunks_per_tensor);
+        const int64_t c = item - (int64_t)t * chunks_per_tensor;
+        const ppq_b200_tensor_desc d = descs[t];
+        const int64_t begin = c * chunk;
+        if (begin >= d.n) continue;                                    // uniform per CTA
+        const int64_t len = (d.n - begin) < chunk ? (d.n - begin) : chunk;
+        MinMax mm;
+        stream_elements(d.x + begin, len, threadIdx.x, kThreads, [&](float v) { mm.add(v); });
+        block_reduce_publish(mm, arena + 2 * (int64_t)d.slot, arena + 2 * (int64_t)d.slot + 1);
+    }
+}
+
+// Per channel: tensor = rows x epc, channel(row) = row % C.  One warp per (row, chunk) work item.
+constexpr int kRowChunk = 4096;
+__global__ void __launch_bounds__(kThreads)
+minmax_c_kernel(const float *__restrict__ x, int64_t rows, int64_t epc, int C, int64_t chunks_per_row,
+                FastDiv div_chunks, FastDiv div_C, float *__restrict__ mins, float *__restrict__ maxs) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (kThreads / 32);
+    const int64_t items = rows * chunks_per_row;
+    for (int64_t item = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); item < items; item += warps) {
+        const int64_t row = (int64_t)div_chunks.quot((uint64_t)item);
+        const int64_t chunk = item - row * chunks_per_row;
+        const int c = (int)(row - (int64_t)div_C.quot((uint64_t)row) * C);
+        const int64_t begin = chunk * kRowChunk;
+        const int64_t len = (epc - begin) < kRowChunk ? (epc - begin) : kRowChunk;
+        MinMax mm;
+        stream_elements(x + row * epc + begin, len, lane, 32, [&](float v) { mm.add(v); });
+        mm.warp_reduce();
+        if (lane == 0) mm.publish(mins + c, maxs + c);
+    }
+}
+
+// ---- histograms -------------------------------------------------------------------------------------------------------
+// Binning operators: return the bin (>= 0) or -1 for "drop".
+struct BinParams { float a, b; int bins, clip; };   // sym: a = hist_scale;  asym: a = min, b = max
+struct SymBin {
+    ExactDiv d; int last; bool clip;
+    __device__ __forceinline__ SymBin(float hist_scale, int bins, bool clip_outliers) : d(hist_scale), last(bins - 1), clip(clip_outliers) {}
+    __device__ __forceinline__ explicit SymBin(const BinParams &p) : SymBin(p.a, p.bins, p.clip != 0) {}
+    __device__ __forceinline__ int finish(float t) const {
+        int b = __float2int_rd(t);                                    // (int) floor(.), saturating, NaN -> 0
+        if (b > last) b = clip ? -1 : last;
+        return b;                                                     // never negative for a positive hist_scale
+    }
+    __device__ __forceinline__ int operator()(float v) const { return finish(d.div(fabsf(v))); }
+    __device__ __forceinline__ int4 bin4(const float4 &v) const {
+        const float4 t = d.div4(make_float4(fabsf(v.x), fabsf(v.y), fabsf(v.z), fabsf(v.w)));
+        return make_int4(finish(t.x), finish(t.y), finish(t.z), finish(t.w));
+    }
+};
+struct AsymBin {
+    ExactDiv d; float vmin; int last; bool clip;
+    __device__ __forceinline__ AsymBin(float mn, float mx, int bins, bool clip_outliers) : vmin(mn), last(bins - 1), clip(clip_outliers) {
+        d.init(__fdiv_rn(__fsub_rn(mx, mn), (float)bins));           // hist_scale = (max - min) / bins, in fp32
+    }
+    __device__ __forceinline__ explicit AsymBin(const BinParams &p) : AsymBin(p.a, p.b, p.bins, p.clip != 0) {}
+    __device__ __forceinline__ int finish(float t) const {
+        int b = __float2int_rd(t);
+        if (b > last) b = clip ? -1 : last;
+        else if (b < 0) b = clip ? -1 : 0;
+        return b;
+    }
+    __device__ __forceinline__ int operator()(float v) const { return finish(d.div(__fsub_rn(v, vmin))); }
+    __device__ __forceinline__ int4 bin4(const float4 &v) const {
+        const float4 t = d.div4(make_float4(__fsub_rn(v.x, vmin), __fsub_rn(v.y, vmin), __fsub_rn(v.z, vmin), __fsub_rn(v.w, vmin)));
+        return make_int4(finish(t.x), finish(t.y), finish(t.z), finish(t.w));
+    }
+};
+
+// Shared-memory privatised counting.  VARIANT 0: bin-0 ballot + smem atomics; 1: plain smem atomics;
+// 2: __match_any_sync aggregation; 3: global atomics straight into `hist` (reference-like, for A/B only).
+template <int VARIANT>
+struct Counter {
+    int *sh; int32_t *gh; int zeros;
+    __device__ __forceinline__ Counter(int *smem_hist, int32_t *global_hist) : sh(smem_hist), gh(global_hist), zeros(0) {}
+    __device__ __forceinline__ void count(int b) {
+        if constexpr (VARIANT == 0) {
+            const unsigned z = __ballot_sync(0xffffffffu, b == 0);
+            if ((threadIdx.x & 31) == 0) zeros += __popc(z);
+            if (b > 0) atomicAdd(sh + b, 1);
+        } else if constexpr (VARIANT == 1) {
+            if (b >= 0) atomicAdd(sh + b, 1);
+        } else if constexpr (VARIANT == 2) {
+            const unsigned peers = __match_any_sync(0xffffffffu, b);
+            if (b >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(sh + b, __popc(peers));
+        } else {
+            if (b >= 0) atomicAdd(gh + b, 1);
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if constexpr (VARIANT == 0) { if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(sh, zeros); }
+    }
+};
+
+template <int VARIANT>
+__device__ __forceinline__ void hist_zero(int *sh, int bins) {
+    if constexpr (VARIANT != 3) {
+        for (int i = threadIdx.x; i < bins; i += kThreads) sh[i] = 0;
+        __syncthreads();
+    }
+}
+template <int VARIANT>
+__device__ __forceinline__ void hist_flush(const int *sh, int bins, int32_t *gh) {
+    if constexpr (VARIANT != 3) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < bins; i += kThreads) {
+            const int v = sh[i];
+            if (v) atomicAdd(gh + i, v);
+        }
+        __syncthreads();
+    }
+}
+
+// The ballot in VARIANT 0/2 needs all 32 lanes of a warp to call count() the same number of times: stream_elements
+// gives every lane of a warp the same trip count except in the ragged tail, so tails are padded with "drop" (-1).
+template <int VARIANT, class Bin>
+__device__ __forceinline__ void hist_stream(const float *__restrict__ x, int64_t n, int64_t first, int64_t stride,
+                                            const Bin &bin, Counter<VARIANT> &cnt) {
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+        const int64_t n4 = n >> 2;
+        const float4 *x4 = reinterpret_cast<const float4 *>(x);
+        const int64_t warp_first = first - (threadIdx.x & 31);              // lane 0 of this warp
+        int64_t i = first;
+        // full unrolled rounds: uniform across the warp because lanes are consecutive in i
+        for (; warp_first + (i - first) + 31 + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
+            float4 v[kUnroll];
+#pragma unroll
+            for (int j = 0; j < kUnroll; j++) v[j] = ld_stream4(x4 + i + j * stride);
+#pragma unroll
+            for (int j = 0; j < kUnroll; j++) { const int4 b = bin.bin4(v[j]); cnt.count(b.x); cnt.count(b.y); cnt.count(b.z); cnt.count(b.w); }
+        }
+        // remaining rounds: warp-uniform loop bound, per-lane predicate
+        for (; warp_first + (i - first) < n4; i += stride) {
+            const bool ok = i < n4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) v = ld_stream4(x4 + i);
+            const int4 b = bin.bin4(v);
+            cnt.count(ok ? b.x : -1); cnt.count(ok ? b.y : -1); cnt.count(ok ? b.z : -1); cnt.count(ok ? b.w : -1);
+        }
+        const int64_t t = (n4 << 2) + first;
+        const bool tail_any = (n4 << 2) + warp_first < n;                    // warp-uniform
+        if (tail_any) cnt.count(t < n ? bin(x[t]) : -1);
+    } else {
+        const int64_t warp_first = first - (threadIdx.x & 31);
+        for (int64_t i = first; warp_first + (i - first) < n; i += stride) cnt.count(i < n ? bin(ld_stream1(x + i)) : -1);
+    }
+}
+
+template <int VARIANT, class Bin>
+__global__ void __launch_bounds__(kThreads)
+histogram_kernel(const float *__restrict__ x, int64_t n, BinParams bp, int32_t *__restrict__ hist) {
+    extern __shared__ int sh[];
+    const int bins = bp.bins;
+    hist_zero<VARIANT>(sh, bins);
+    Counter<VARIANT> cnt(sh, hist);
+    const Bin bin(bp);
+    hist_stream<VARIANT>(x, n, (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads, bin, cnt);
+    cnt.finish();
+    hist_flush<VARIANT>(sh, bins, hist);
+}
+
+// hist_scale read from device memory (phase 2 without a host round trip)
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads)
+histogram_dscale_kernel(const float *__restrict__ x, int64_t n, const float *__restrict__ hist_scale, int clip, int bins,
+                        int32_t *__restrict__ hist) {
+    extern __shared__ int sh[];
+    hist_zero<VARIANT>(sh, bins);
+    Counter<VARIANT> cnt(sh, hist);
+    const SymBin bin(__ldg(hist_scale), bins, clip != 0);
+    hist_stream<VARIANT>(x, n, (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads, bin, cnt);
+    cnt.finish();
+    hist_flush<VARIANT>(sh, bins, hist);
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads)
+multi_histogram_t_kernel(const ppq_b200_tensor_desc *__restrict__ descs, int count, int64_t chunk, int chunks_per_tensor,
+                         const float *__restrict__ hist_scale_arena, int clip, int bins, int32_t *__restrict__ hist_arena) {
+    extern __shared__ int sh[];
+    const int64_t items = (int64_t)count * chunks_per_tensor;
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int t = (int)(item / chunks_per_tensor);
+        const int64_t c = item - (int64_t)t * chunks_per_tensor;
+        const ppq_b200_tensor_desc d = descs[t];
+        const int64_t begin = c * chunk;
+        if (begin >= d.n) continue;
+        const int64_t len = (d.n - begin) < chunk ? (d.n - begin) : chunk;
+        int32_t *gh = hist_arena + (int64_t)d.slot * bins;
+        hist_zero<VARIANT>(sh, bins);
+        Counter<VARIANT> cnt(sh, gh);
+        const SymBin bin(__ldg(hist_scale_arena + d.slot), bins, clip != 0);
+        hist_stream<VARIANT>(d.x + begin, len, threadIdx.x, kThreads, bin, cnt);
+        cnt.finish();
+        hist_flush<VARIANT>(sh, bins, gh);
+    }
+}
+
+// Per-channel histogram: rows x epc, hist[c][bins].  One CTA per (row, chunk); smem holds that row's private bins.
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads)
+histogram_c_kernel(const float *__restrict__ x, int64_t rows, int64_t epc, int C, int64_t chunk, int64_t chunks_per_row,
+                   float hist_scale, int clip, int bins, int32_t *__restrict__ hist) {
+    extern __shared__ int sh[];
+    const int64_t items = rows * chunks_per_row;
+    const SymBin bin(hist_scale, bins, clip != 0);
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int64_t row = item / chunks_per_row;
+        const int64_t c0 = item - row * chunks_per_row;
+        const int ch = (int)(row % C);
+        const int64_t begin = c0 * chunk;
+        const int64_t len = (epc - begin) < chunk ? (epc - begin) : chunk;
+        int32_t *gh = hist + (int64_t)ch * bins;
+        hist_zero<VARIANT>(sh, bins);
+        Counter<VARIANT> cnt(sh, gh);
+        hist_stream<VARIANT>(x + row * epc + begin, len, threadIdx.x, kThreads, bin, cnt);
+        cnt.finish();
+        hist_flush<VARIANT>(sh, bins, gh);
+    }
+}
+
+// ---- launch helpers -------------------------------------------------------------------------------------------------------
+constexpr int kMaxSmemBins = 12288;            // 48 KB of int32 without opting in to larger dynamic shared memory
+
+// Elements each CTA should own before paying for zeroing + flushing `bins` counters.
+static inline int hist_grid(int64_t n, int bins) {
+    const int64_t per_cta = (int64_t)bins * 8 > 32768 ? (int64_t)bins * 8 : 32768;
+    int64_t g = (n + per_cta - 1) / per_cta;
+    const int64_t cap = (int64_t)kSMs * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+template <class Bin>
+static int launch_hist(const float *x, int64_t n, const BinParams &bin, int64_t bins, int32_t *hist, cudaStream_t st) {
+    int var = variant_of(kVarHistogram);
+    if (bins > kMaxSmemBins) var = 3;
+    const int grid = var == 3 ? grid_for(n, kThreads, 16, 8) : hist_grid(n, (int)bins);
+    const size_t smem = var == 3 ? 0 : (size_t)bins * sizeof(int);
+    switch (var) {
+    case 1:  histogram_kernel<1, Bin><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
+    case 2:  histogram_kernel<2, Bin><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
+    case 3:  histogram_kernel<3, Bin><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
+    default: histogram_kernel<0, Bin><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ppqb
+
+using namespace ppqb;
+
+extern "C" {
+
+int ppq_b200_minmax_init(float *mins, float *maxs, int64_t count, void *stream) {
+    if (count <= 0 || (!mins && !maxs)) return (int)cudaErrorInvalidValue;
+    minmax_init_kernel<<<(int)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mins, maxs, count);
+    return (int)cudaGetLastError();
+}
+
+int ppq_b200_minmax_t(const float *x, int64_t n, float *minmax, void *stream) {
+    if (n <= 0 || !x || !minmax) return (int)cudaErrorInvalidValue;
+    const int grid = grid_for((n + 3) / 4, kThreads, kUnroll * 4, 8);
+    minmax_t_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, n, minmax);
+    return (int)cudaGetLastError();
+}
+
+int ppq_b200_minmax_c(const float *x, int64_t n, int64_t epc, int C, float *mins, float *maxs, void *stream) {
+    if (n <= 0 || epc <= 0 || C <= 0 || !x || !mins || !maxs || n % epc != 0) return (int)cudaErrorInvalidValue;
+    const int64_t rows = n / epc;
+    const int64_t chunks = (epc + kRowChunk - 1) / kRowChunk;
+    if (chunks > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+    const int64_t items = rows * chunks;
+    int64_t grid = (items + (kThreads / 32) - 1) / (kThreads / 32);
+    if (grid > (int64_t)kSMs * 8) grid = (int64_t)kSMs * 8;
+    minmax_c_kernel<<<(int)grid, kThreads, 0, (cudaStream_t)stream>>>(x, rows, epc, C, chunks, FastDiv((uint32_t)chunks),
+                                                                          FastDiv((uint32_t)C), mins, maxs);
+    return (int)cudaGetLastError();
+}
+
+int ppq_b200_histogram_t(const float *x, int64_t n, float hist_scale, int clip_outliers, int32_t *hist, int64_t bins, void *stream) {
+    if (n <= 0 || !x || !hist || bins <= 0 || bins > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+    return launch_hist<SymBin>(x, n, BinParams{hist_scale, 0.f, (int)bins, clip_outliers}, bins, hist, (cudaStream_t)stream);
+}
+
+int ppq_b200_histogram_asym_t(const float *x, int64_t n, float vmin, float vmax, int clip_outliers, int32_t *hist, int64_t bins,
+                              void *stream) {
+    if (n <= 0 || !x || !hist || bins <= 0 || bins > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+    return launch_hist<AsymBin>(x, n, BinParams{vmin, vmax, (int)bins, clip_outliers}, bins, hist, (cudaStream_t)stream);
+}
+
+int ppq_b200_histogram_t_dscale(const float *x, int64_t n, const float *hist_scale_dev, int clip_outliers, int32_t *hist,
+                                int64_t bins, void *stream) {
+    if (n <= 0 || !x || !hist || !hist_scale_dev || bins <= 0 || bins > kMaxSmemBins) return (int)cudaErrorInvalidValue;
+    const int grid = hist_grid(n, (int)bins);
+    histogram_dscale_kernel<0><<<grid, kThreads, (size_t)bins * sizeof(int), (cudaStream_t)stream>>>(
+        x, n, hist_scale_dev, clip_outliers, (int)bins, hist);
+    return (int)cudaGetLastError();
+}
+
+int ppq_b200_histogram_c(const float *x, int64_t n, int64_t epc, int C, float hist_scale, int clip_outliers, int32_t *hist,
+                         int64_t bins, void *stream) {
+    if (n <= 0 || epc <= 0 || C <= 0 || !x || !hist || bins <= 0 || bins > kMaxSmemBins || n % epc != 0)
+        return (int)cudaErrorInvalidValue;
+    const int64_t rows = n / epc;
+    const int64_t chunk = (int64_t)bins * 8 > 32768 ? (int64_t)bins * 8 : 32768;
+    const int64_t chunks = (epc + chunk - 1) / chunk;
+    const int64_t items = rows * chunks;
+    const int grid = (int)(items < (int64_t)kSMs * 8 ? items : (int64_t)kSMs * 8);
+    histogram_c_kernel<0><<<grid, kThreads, (size_t)bins * sizeof(int), (cudaStream_t)stream>>>(
+        x, rows, epc, C, chunk, chunks, hist_scale, clip_outliers, (int)bins, hist);
+    return (int)cudaGetLastError();
+}
+
+int ppq_b200_multi_minmax_t(const ppq_b200_tensor_desc *descs, int count, int64_t max_n, float *minmax_arena, void *stream) {
+    if (count <= 0 || max_n <= 0 || !descs || !minmax_arena) return (int)cudaErrorInvalidValue;
+    const int64_t chunk = 65536;
+    const int64_t cpt = (max_n + chunk - 1) / chunk;
+    if (cpt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+    const int64_t items = (int64_t)count * cpt;
+    const int grid = (int)(items < (int64_t)kSMs * 8 ? items : (int64_t)kSMs * 8);
+    multi_minmax_t_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(descs, count, chunk, (int)cpt, minmax_arena);
+    return (int)cudaGetLastError();
+}
+
+int ppq_b200_multi_histogram_t(const ppq_b200_tensor_desc *descs, int count, int64_t max_n, const float *hist_scale_arena,
+                               int clip_outliers, int32_t *hist_arena, int64_t bins, void *stream) {
+    if (count <= 0 || max_n <= 0 || !descs || !hist_scale_arena || !hist_arena || bins <= 0 || bins > kMaxSmemBins)
+        return (int)cudaErrorInvalidValue;
+    const int64_t chunk = (int64_t)bins * 16 > 65536 ? (int64_t)bins * 16 : 65536;
+    const int64_t cpt = (max_n + chunk - 1) / chunk;
+    if (cpt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+    const int64_t items = (int64_t)count * cpt;
+    const int grid = (int)(items < (int64_t)kSMs * 8 ? items : (int64_t)kSMs * 8);
+    multi_histogram_t_kernel<0><<<grid, kThreads, (size_t)bins * sizeof(int), (cudaStream_t)stream>>>(
+        descs, count, chunk, (int)cpt, hist_scale_arena, clip_outliers, (int)bins, hist_arena);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,217 @@
+// search.cu -- scale / offset search on the device (sm_100a), behind the C ABI of include/ppq_b200.h.
+//
+//   ppq_b200_minmax_to_scale_offset   replaces minmax_to_scale_offset   (/root/reference/ppq/quantization/observer/range.py:22-75)
+//   ppq_b200_hist_scale_from_minmax   replaces the phase-1 render of TorchHistObserver (range.py:291-301)
+//   ppq_b200_kl_search                replaces TorchHistObserver.hist_to_scale_offset (range.py:190-282) +
+//                                     torch_KL_divergence (ppq/quantization/measure/statistic.py:3-12)
+//   ppq_b200_mse_search               replaces TorchMSEObserver.hist_to_scale_offset (range.py:456-520) driving
+//                                     compute_mse_loss (ppq/csrc/cpu/hist_mse.cc:3-28)
+//
+// These are tiny (O(tensors x bins)) but they keep the render phase of the calibration on the device: no .item() per
+// tensor, no per-channel Python loop, and the histogram arena never has to leave HBM before the all-reduce.
+// Arithmetic follows the Python originals: fp64 for the scale/offset algebra (Python floats), fp32 histograms and fp64
+// log10 for the KL divergence.
+#include "common.cuh"
+#include "../../include/ppq_b200.h"
+
+namespace ppqb {
+
+// ppq_numerical_round(v, ROUND_HALF_EVEN) on a double (utils/round.py:78: Decimal.quantize half-even == rint).
+__device__ __forceinline__ double round_half_even(double v) { return rint(v); }
+
+// ppq_round_to_power_of_2 (utils/round.py:115-135): 2^round(log2(x)); ROUND_UP = ceil, ROUND_HALF_UP on the exponent.
+__device__ __forceinline__ double pow2_round(double v, bool half_up) {
+    if (v == 0.0) return 0.0;
+    const double sign = v >= 0.0 ? 1.0 : -1.0;
+    const double l = log2(sign * v);
+    double e;
+    if (!half_up) e = ceil(l);
+    else {
+        // Decimal ROUND_HALF_UP for positive exponents, ROUND_HALF_DOWN for negative ones (utils/round.py:80-82)
+        const double f = floor(l), frac = l - f;
+        if (frac > 0.5) e = f + 1.0; else if (frac < 0.5) e = f; else e = (l > 0.0) ? f + 1.0 : f;
+    }
+    return sign * exp2(e);
+}
+
+struct ScaleOffset { double scale, offset; };
+__device__ __forceinline__ ScaleOffset minmax_to_scale_offset_dev(double mn, double mx, int qmin, int qmax, bool sym, bool pow2,
+                                                                  double min_scale) {
+    if (mn > 0.0) mn = 0.0;
+    if (mx < 0.0) mx = 0.0;
+    ScaleOffset r;
+    const double levels = (double)(qmax - qmin);
+    if (sym) {
+        const double range = 2.0 * fmax(fabs(mx), fabs(mn));
+        r.scale = fmax(range / levels, min_scale);
+        r.offset = 0.0;
+    } else {
+        const double range = mx - mn;
+        r.scale = fmax(range / levels, min_scale);
+        r.offset = round_half_even(-mn / r.scale);
+    }
+    if (pow2) r.scale = pow2_round(r.scale, false);
+    return r;
+}
+
+__global__ void minmax_to_scale_offset_kernel(const float *__restrict__ mins, const float *__restrict__ maxs, int64_t count,
+                                              int64_t stride, int qmin, int qmax, int sym, int pow2, double min_scale,
+                                              float *__restrict__ scale, float *__restrict__ offset) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const ScaleOffset r = minmax_to_scale_offset_dev((double)mins[i * stride], (double)maxs[i * stride], qmin, qmax, sym != 0,
+                                                     pow2 != 0, min_scale);
+    scale[i] = (float)r.scale;
+    offset[i] = (float)r.offset;
+}
+
+__global__ void hist_scale_kernel(const float *__restrict__ minmax, int64_t count, int sym, int64_t bins, float *__restrict__ hs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double mn = (double)minmax[2 * i], mx = (double)minmax[2 * i + 1];
+    const double range = sym ? fmax(fabs(mx), fabs(mn)) : (mx - mn);
+    hs[i] = (float)(range / (double)bins);
+}
+
+// ---- KL search: one CTA per histogram ---------------------------------------------------------------------------------------
+constexpr int kKlThreads = 512;
+
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) scratch[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < kKlThreads / 32; i++) t += scratch[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(kKlThreads)
+kl_search_kernel(const int32_t *__restrict__ hist_arena, int bins, const float *__restrict__ hist_scale_arena,
+                 const float *__restrict__ minmax_arena, int num_of_bits, int pow2, double min_scale, float *__restrict__ scale_out, int32_t *__restrict__ best_out) {
+    extern __shared__ unsigned char kl_smem[];
+    float *h = reinterpret_cast<float *>(kl_smem);                    // [bins]   the edited histogram as fp32
+    double *pre = reinterpret_cast<double *>(kl_smem + (((size_t)bins * 4 + 7) & ~(size_t)7));   // [bins + 1] exclusive prefix sums
+    float *gval = reinterpret_cast<float *>(pre + bins + 1);          // [quant_bins] per-group spread value
+    __shared__ double scratch[kKlThreads / 32];
+    __shared__ double s_best_loss; __shared__ int s_best;
+
+    const int32_t *hist = hist_arena + (int64_t)blockIdx.x * bins;
+    const int quant_bins = 1 << (num_of_bits - 1);
+    const int dead = (int)((double)bins * .002);                      // int(hist_bins * .002)
+    for (int i = threadIdx.x; i < bins; i += kKlThreads) {
+        float v = (float)hist[i];
+        if (i < dead) v = 0.f;
+        if (i == dead) v = 1.f;
+        h[i] = v;
+    }
+    __syncthreads();
+    // exclusive prefix sums (integer-valued counts: exact in fp64); serial per 64-bin segment, then segment offsets
+    {
+        const int seg = (bins + kKlThreads - 1) / kKlThreads;
+        const int b0 = threadIdx.x * seg, b1 = min(bins, b0 + seg);
+        double s = 0.0;
+        for (int i = b0; i < b1; i++) s += (double)h[i];
+        // inclusive scan of the per-thread totals through shared memory
+        double *tot = pre;                                            // reuse: pre[0..kKlThreads) temporarily
+        __syncthreads();
+        tot[threadIdx.x] = s;
+        __syncthreads();
+        double base = 0.0;
+        for (int t = 0; t < (int)threadIdx.x; t++) base += tot[t];
+        __syncthreads();
+        double run = base;
+        for (int i = b0; i < b1; i++) { const double v = (double)h[i]; pre[i] = run; run += v; }
+        if (b1 == bins && b0 < bins) pre[bins] = run;
+        if (bins == 0 && threadIdx.x == 0) pre[0] = 0.0;
+        __syncthreads();
+    }
+    const float total = (float)pre[bins];                            // torch.sum(histogram) (fp32 tensor)
+    if (threadIdx.x == 0) { s_best_loss = 0.0; s_best = -1; }
+
+    for (int br = quant_bins; br < bins + quant_bins - 1; br += quant_bins) {
+        if (br > bins) break;                                         // range() upstream never exceeds bins for bins % quant_bins == 0
+        const int ratio = br / quant_bins;
+        // group statistics: spread value = (sum of the group) / (number of non-empty bins), fp32 like torch.div
+        for (int g = threadIdx.x; g < quant_bins; g += kKlThreads) {
+            const int a = g * ratio;
+            int cnt = 0;
+            for (int i = a; i < a + ratio; i++) cnt += h[i] > 0.f;
+            const float gsum = (float)(pre[a + ratio] - pre[a]);
+            gval[g] = __fdiv_rn(gsum, (float)(cnt == 0 ? 1 : cnt));
+        }
+        __syncthreads();
+        // normaliser of q: sum over non-empty bins of their group's spread value
+        double qs = 0.0;
+        for (int i = threadIdx.x; i < br; i += kKlThreads) if (h[i] > 0.f) qs += (double)gval[i / ratio];
+        const float qsum = (float)block_sum(qs, scratch);
+        const float tail = (float)(pre[bins] - pre[br]);              // torch.sum(histogram[bin_range:])
+        double kl = 0.0;
+        for (int i = threadIdx.x; i < br; i += kKlThreads) {
+            float pv = h[i];
+            if (i == br - 1) pv = __fadd_rn(pv, tail);
+            const float p = __fdiv_rn(pv, total);
+            if (p == 0.f) continue;                                   // 0 * (finite) contributes exactly 0
+            const float q = h[i] > 0.f ? __fdiv_rn(gval[i / ratio], qsum) : 0.f;
+            kl += (double)p * (log10((double)p + 1e-30) - log10((double)q + 1e-30));
+        }
+        kl = block_sum(kl, scratch);
+        if (threadIdx.x == 0 && (s_best < 0 || kl < s_best_loss)) { s_best = br; s_best_loss = kl; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double hs;
+        if (minmax_arena) {
+            const double mn = (double)minmax_arena[2 * blockIdx.x], mx = (double)minmax_arena[2 * blockIdx.x + 1];
+            hs = fmax(fabs(mx), fabs(mn)) / (double)bins;            // the Python double of range.py:294-300
+        } else hs = (double)hist_scale_arena[blockIdx.x];
+        double scale = ((double)s_best / (double)bins) * hs * ((double)bins / (double)quant_bins);
+        scale = fmax(scale, min_scale);
+        if (pow2) scale = pow2_round(scale, true);
+        scale_out[blockIdx.x] = (float)scale;
+        if (best_out) best_out[blockIdx.x] = s_best;
+    }
+}
+
+}  // namespace ppqb
+
+using namespace ppqb;
+
+extern "C" {
+
+int ppq_b200_minmax_to_scale_offset(const float *mins, const float *maxs, int64_t count, int64_t stride, int qmin, int qmax,
+                                    int symmetrical, int power_of_2, double min_scale, float *scale, float *offset, void *stream) {
+    if (count <= 0 || stride <= 0 || !mins || !maxs || !scale || !offset || qmax <= qmin) return (int)cudaErrorInvalidValue;
+    minmax_to_scale_offset_kernel<<<(int)((count + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        mins, maxs, count, stride, qmin, qmax, symmetrical, power_of_2, min_scale, scale, offset);
+    return (int)cudaGetLastError();
+}
+
+int ppq_b200_hist_scale_from_minmax(const float *minmax_arena, int64_t count, int symmetrical, int64_t bins, float *hist_scale_arena,
+                                    void *stream) {
+    if (count <= 0 || bins <= 0 || !minmax_arena || !hist_scale_arena) return (int)cudaErrorInvalidValue;
+    hist_scale_kernel<<<(int)((count + 127) / 128), 128, 0, (cudaStream_t)stream>>>(minmax_arena, count, symmetrical, bins, hist_scale_arena);
+    return (int)cudaGetLastError();
+}
+
+int ppq_b200_kl_search(const int32_t *hist_arena, int64_t count, int64_t bins, const float *hist_scale_arena,
+                       const float *minmax_arena, int num_of_bits, int power_of_2, double min_scale, float *scale_out, int32_t *best_bin_range_out, void *stream) {
+    if (count <= 0 || count > 0x7fffffffLL || !hist_arena || (!hist_scale_arena && !minmax_arena) || !scale_out)
+        return (int)cudaErrorInvalidValue;
+    if (num_of_bits < 2 || num_of_bits > 16) return (int)cudaErrorInvalidValue;
+    const int64_t qb = 1ll << (num_of_bits - 1);
+    if (bins < qb || bins > 16384 || bins < kKlThreads) return (int)cudaErrorInvalidValue;
+    const size_t smem = (((size_t)bins * 4 + 7) & ~(size_t)7) + (size_t)(bins + 1) * 8 + (size_t)qb * 4;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kl_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        configured = true;
+    }
+    kl_search_kernel<<<(int)count, kKlThreads, smem, (cudaStream_t)stream>>>(hist_arena, (int)bins, hist_scale_arena, minmax_arena,
+                                                                               num_of_bits, power_of_2, min_scale, scale_out, best_bin_range_out);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"
