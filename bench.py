@@ -112,30 +112,50 @@ class Workload:
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler(threading.Thread):
-    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    """SM clock + throttle reasons sampled DURING the timed region through NVML (nvidia-smi's own source; a subprocess per
+    sample would be slower than the whole timed region)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.err = index, [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:                                            # noqa: BLE001
+            self.nv, self.err = None, f'{type(e).__name__}: {e}'
+
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            parts = [p for p in vis.split(',') if p.strip()]
+            if i < len(parts) and parts[i].strip().isdigit(): return int(parts[i])
+        return i
 
     def run(self):
+        if self.nv is None: return
+        nv = self.nv
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out: self.samples.append([c.strip() for c in out.split(',')])
-            except Exception:
-                pass
-            time.sleep(0.1)
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons')
+                                     else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+            except Exception as e:                                        # noqa: BLE001
+                self.err = f'{type(e).__name__}: {e}'
+                break
+            time.sleep(0.001)
 
     def summary(self):
-        if not self.samples: return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith('active')})
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                'reasons': reasons, 'samples': len(self.samples)}
+        if not self.samples: return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable: ' + str(self.err)]}
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
+        for s in self.samples: bits |= int(s[1])
+        names = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap', 0x80: 'hw_power_brake_slowdown'}
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': self.max_sm, 'reasons': sorted(n for b, n in names.items() if bits & b),
+                'samples': len(self.samples)}
 
 
 def measured_peaks():
@@ -227,7 +247,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         result['fakequant'] = fakequant_sweep(ext, device, peak)
         result['e2e'] = run_e2e(args, device, world) if not args.no_e2e else None
-        result['cpu_baseline'] = cpu_baseline(args, sample_steps=2)
+        result['cpu_baseline'] = cpu_baseline(args, sample_steps=1)
     elif not args.no_e2e:
         run_e2e(args, device, world)
     return result

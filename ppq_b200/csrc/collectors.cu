@@ -143,71 +143,69 @@ minmax_c_kernel(const float *__restrict__ x, int64_t rows, int64_t epc, int C, i
 }
 
 // ---- histograms -------------------------------------------------------------------------------------------------------
-// Binning operators: return the bin (>= 0) or -1 for "drop".
+// Binning operators map a value to a slot of the CTA-private shared histogram: slots 0..bins-1 are the bins, slot `bins`
+// is a trash slot for dropped samples, so that the shared atomic is unconditional (no branch per element; ptxas turns
+// `red.shared.add.u32 [a], 1` into ATOMS.POPC.INC, which aggregates same-address lanes of a warp in hardware -- the
+// post-ReLU pile-up in bin 0 costs one pass, not 32).
 struct BinParams { float a, b; int bins, clip; };   // sym: a = hist_scale;  asym: a = min, b = max
 struct SymBin {
-    ExactDiv d; int last; bool clip;
-    __device__ __forceinline__ SymBin(float hist_scale, int bins, bool clip_outliers) : d(hist_scale), last(bins - 1), clip(clip_outliers) {}
+    ExactDiv d; unsigned bins; int last; bool clip;
+    __device__ __forceinline__ SymBin(float hist_scale, int nbins, bool clip_outliers) : bins(nbins), last(nbins - 1), clip(clip_outliers) { d.init(hist_scale); }
     __device__ __forceinline__ explicit SymBin(const BinParams &p) : SymBin(p.a, p.bins, p.clip != 0) {}
-    __device__ __forceinline__ int finish(float t) const {
-        int b = __float2int_rd(t);                                    // (int) floor(.), saturating, NaN -> 0
-        if (b > last) b = clip ? -1 : last;
-        return b;                                                     // never negative for a positive hist_scale
+    __device__ __forceinline__ unsigned finish(float t) const {
+        const int b = __float2int_rd(t);                              // (int) floor(.), saturating, NaN -> 0; never negative here
+        return clip ? min((unsigned)b, bins) : (unsigned)min(b, last);
     }
-    __device__ __forceinline__ int operator()(float v) const { return finish(d.div(fabsf(v))); }
-    __device__ __forceinline__ int4 bin4(const float4 &v) const {
+    __device__ __forceinline__ unsigned operator()(float v) const { return finish(d.div(fabsf(v))); }
+    __device__ __forceinline__ uint4 bin4(const float4 &v) const {
         const float4 t = d.div4(make_float4(fabsf(v.x), fabsf(v.y), fabsf(v.z), fabsf(v.w)));
-        return make_int4(finish(t.x), finish(t.y), finish(t.z), finish(t.w));
+        return make_uint4(finish(t.x), finish(t.y), finish(t.z), finish(t.w));
     }
 };
 struct AsymBin {
-    ExactDiv d; float vmin; int last; bool clip;
-    __device__ __forceinline__ AsymBin(float mn, float mx, int bins, bool clip_outliers) : vmin(mn), last(bins - 1), clip(clip_outliers) {
-        d.init(__fdiv_rn(__fsub_rn(mx, mn), (float)bins));           // hist_scale = (max - min) / bins, in fp32
+    ExactDiv d; float vmin; unsigned bins; int last; bool clip;
+    __device__ __forceinline__ AsymBin(float mn, float mx, int nbins, bool clip_outliers) : vmin(mn), bins(nbins), last(nbins - 1), clip(clip_outliers) {
+        d.init(__fdiv_rn(__fsub_rn(mx, mn), (float)nbins));           // hist_scale = (max - min) / bins, in fp32
     }
     __device__ __forceinline__ explicit AsymBin(const BinParams &p) : AsymBin(p.a, p.b, p.bins, p.clip != 0) {}
-    __device__ __forceinline__ int finish(float t) const {
-        int b = __float2int_rd(t);
-        if (b > last) b = clip ? -1 : last;
-        else if (b < 0) b = clip ? -1 : 0;
-        return b;
+    __device__ __forceinline__ unsigned finish(float t) const {
+        const int b = __float2int_rd(t);
+        return clip ? min((unsigned)b, bins) : (unsigned)max(min(b, last), 0);   // negative b wraps above `bins` -> trash
     }
-    __device__ __forceinline__ int operator()(float v) const { return finish(d.div(__fsub_rn(v, vmin))); }
-    __device__ __forceinline__ int4 bin4(const float4 &v) const {
+    __device__ __forceinline__ unsigned operator()(float v) const { return finish(d.div(__fsub_rn(v, vmin))); }
+    __device__ __forceinline__ uint4 bin4(const float4 &v) const {
         const float4 t = d.div4(make_float4(__fsub_rn(v.x, vmin), __fsub_rn(v.y, vmin), __fsub_rn(v.z, vmin), __fsub_rn(v.w, vmin)));
-        return make_int4(finish(t.x), finish(t.y), finish(t.z), finish(t.w));
+        return make_uint4(finish(t.x), finish(t.y), finish(t.z), finish(t.w));
     }
 };
 
-// Shared-memory privatised counting.  VARIANT 0: bin-0 ballot + smem atomics; 1: plain smem atomics;
-// 2: __match_any_sync aggregation; 3: global atomics straight into `hist` (reference-like, for A/B only).
+// Counting into the CTA-private histogram.
+//   VARIANT 0 (default): unconditional red.shared.add through a precomputed 32-bit shared-window address.
+//   VARIANT 1: the same through generic-pointer atomicAdd;  VARIANT 2: __match_any_sync aggregation in software;
+//   VARIANT 3: global atomics straight into `hist` (what the reference does; kept for A/B measurements only).
 template <int VARIANT>
 struct Counter {
-    int *sh; int32_t *gh; int zeros;
-    __device__ __forceinline__ Counter(int *smem_hist, int32_t *global_hist) : sh(smem_hist), gh(global_hist), zeros(0) {}
-    __device__ __forceinline__ void count(int b) {
+    int *sh; int32_t *gh; uint32_t sh_addr; unsigned trash;
+    __device__ __forceinline__ Counter(int *smem_hist, int32_t *global_hist, int bins)
+        : sh(smem_hist), gh(global_hist), sh_addr((uint32_t)__cvta_generic_to_shared(smem_hist)), trash(bins) {}
+    __device__ __forceinline__ void count(unsigned slot) {
         if constexpr (VARIANT == 0) {
-            const unsigned z = __ballot_sync(0xffffffffu, b == 0);
-            if ((threadIdx.x & 31) == 0) zeros += __popc(z);
-            if (b > 0) atomicAdd(sh + b, 1);
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(sh_addr + slot * 4u) : "memory");
         } else if constexpr (VARIANT == 1) {
-            if (b >= 0) atomicAdd(sh + b, 1);
+            atomicAdd(sh + slot, 1);
         } else if constexpr (VARIANT == 2) {
-            const unsigned peers = __match_any_sync(0xffffffffu, b);
-            if (b >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(sh + b, __popc(peers));
+            const unsigned peers = __match_any_sync(0xffffffffu, slot);
+            if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(sh + slot, __popc(peers));
         } else {
-            if (b >= 0) atomicAdd(gh + b, 1);
+            if (slot != trash) atomicAdd(gh + slot, 1);
         }
-    }
-    __device__ __forceinline__ void finish() {
-        if constexpr (VARIANT == 0) { if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(sh, zeros); }
     }
 };
 
 template <int VARIANT>
 __device__ __forceinline__ void hist_zero(int *sh, int bins) {
     if constexpr (VARIANT != 3) {
-        for (int i = threadIdx.x; i < bins; i += kThreads) sh[i] = 0;
+        for (int i = threadIdx.x; i <= bins; i += kThreads) sh[i] = 0;      // + the trash slot
         __syncthreads();
     }
 }
@@ -239,22 +237,22 @@ __device__ __forceinline__ void hist_stream(const float *__restrict__ x, int64_t
 #pragma unroll
             for (int j = 0; j < kUnroll; j++) v[j] = ld_stream4(x4 + i + j * stride);
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) { const int4 b = bin.bin4(v[j]); cnt.count(b.x); cnt.count(b.y); cnt.count(b.z); cnt.count(b.w); }
+            for (int j = 0; j < kUnroll; j++) { const uint4 b = bin.bin4(v[j]); cnt.count(b.x); cnt.count(b.y); cnt.count(b.z); cnt.count(b.w); }
         }
         // remaining rounds: warp-uniform loop bound, per-lane predicate
         for (; warp_first + (i - first) < n4; i += stride) {
             const bool ok = i < n4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok) v = ld_stream4(x4 + i);
-            const int4 b = bin.bin4(v);
-            cnt.count(ok ? b.x : -1); cnt.count(ok ? b.y : -1); cnt.count(ok ? b.z : -1); cnt.count(ok ? b.w : -1);
+            const uint4 b = bin.bin4(v);
+            cnt.count(ok ? b.x : cnt.trash); cnt.count(ok ? b.y : cnt.trash); cnt.count(ok ? b.z : cnt.trash); cnt.count(ok ? b.w : cnt.trash);
         }
         const int64_t t = (n4 << 2) + first;
         const bool tail_any = (n4 << 2) + warp_first < n;                    // warp-uniform
-        if (tail_any) cnt.count(t < n ? bin(x[t]) : -1);
+        if (tail_any) cnt.count(t < n ? bin(x[t]) : cnt.trash);
     } else {
         const int64_t warp_first = first - (threadIdx.x & 31);
-        for (int64_t i = first; warp_first + (i - first) < n; i += stride) cnt.count(i < n ? bin(ld_stream1(x + i)) : -1);
+        for (int64_t i = first; warp_first + (i - first) < n; i += stride) cnt.count(i < n ? bin(ld_stream1(x + i)) : cnt.trash);
     }
 }
 
@@ -264,10 +262,9 @@ histogram_kernel(const float *__restrict__ x, int64_t n, BinParams bp, int32_t *
     extern __shared__ int sh[];
     const int bins = bp.bins;
     hist_zero<VARIANT>(sh, bins);
-    Counter<VARIANT> cnt(sh, hist);
+    Counter<VARIANT> cnt(sh, hist, bins);
     const Bin bin(bp);
     hist_stream<VARIANT>(x, n, (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads, bin, cnt);
-    cnt.finish();
     hist_flush<VARIANT>(sh, bins, hist);
 }
 
@@ -278,10 +275,9 @@ histogram_dscale_kernel(const float *__restrict__ x, int64_t n, const float *__r
                         int32_t *__restrict__ hist) {
     extern __shared__ int sh[];
     hist_zero<VARIANT>(sh, bins);
-    Counter<VARIANT> cnt(sh, hist);
+    Counter<VARIANT> cnt(sh, hist, bins);
     const SymBin bin(__ldg(hist_scale), bins, clip != 0);
     hist_stream<VARIANT>(x, n, (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads, bin, cnt);
-    cnt.finish();
     hist_flush<VARIANT>(sh, bins, hist);
 }
 
@@ -300,10 +296,9 @@ multi_histogram_t_kernel(const ppq_b200_tensor_desc *__restrict__ descs, int cou
         const int64_t len = (d.n - begin) < chunk ? (d.n - begin) : chunk;
         int32_t *gh = hist_arena + (int64_t)d.slot * bins;
         hist_zero<VARIANT>(sh, bins);
-        Counter<VARIANT> cnt(sh, gh);
+        Counter<VARIANT> cnt(sh, gh, bins);
         const SymBin bin(__ldg(hist_scale_arena + d.slot), bins, clip != 0);
         hist_stream<VARIANT>(d.x + begin, len, threadIdx.x, kThreads, bin, cnt);
-        cnt.finish();
         hist_flush<VARIANT>(sh, bins, gh);
     }
 }
@@ -324,15 +319,14 @@ histogram_c_kernel(const float *__restrict__ x, int64_t rows, int64_t epc, int C
         const int64_t len = (epc - begin) < chunk ? (epc - begin) : chunk;
         int32_t *gh = hist + (int64_t)ch * bins;
         hist_zero<VARIANT>(sh, bins);
-        Counter<VARIANT> cnt(sh, gh);
+        Counter<VARIANT> cnt(sh, gh, bins);
         hist_stream<VARIANT>(x + row * epc + begin, len, threadIdx.x, kThreads, bin, cnt);
-        cnt.finish();
         hist_flush<VARIANT>(sh, bins, gh);
     }
 }
 
 // ---- launch helpers -------------------------------------------------------------------------------------------------------
-constexpr int kMaxSmemBins = 12288;            // 48 KB of int32 without opting in to larger dynamic shared memory
+constexpr int kMaxSmemBins = 12287;            // (bins + 1) int32 slots within the default 48 KB of dynamic shared memory
 
 // Elements each CTA should own before paying for zeroing + flushing `bins` counters.
 static inline int hist_grid(int64_t n, int bins) {
@@ -349,7 +343,7 @@ static int launch_hist(const float *x, int64_t n, const BinParams &bin, int64_t 
     int var = variant_of(kVarHistogram);
     if (bins > kMaxSmemBins) var = 3;
     const int grid = var == 3 ? grid_for(n, kThreads, 16, 8) : hist_grid(n, (int)bins);
-    const size_t smem = var == 3 ? 0 : (size_t)bins * sizeof(int);
+    const size_t smem = var == 3 ? 0 : (size_t)(bins + 1) * sizeof(int);
     switch (var) {
     case 1:  histogram_kernel<1, Bin><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
     case 2:  histogram_kernel<2, Bin><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
@@ -406,7 +400,7 @@ int ppq_b200_histogram_t_dscale(const float *x, int64_t n, const float *hist_sca
                                 int64_t bins, void *stream) {
     if (n <= 0 || !x || !hist || !hist_scale_dev || bins <= 0 || bins > kMaxSmemBins) return (int)cudaErrorInvalidValue;
     const int grid = hist_grid(n, (int)bins);
-    histogram_dscale_kernel<0><<<grid, kThreads, (size_t)bins * sizeof(int), (cudaStream_t)stream>>>(
+    histogram_dscale_kernel<0><<<grid, kThreads, (size_t)(bins + 1) * sizeof(int), (cudaStream_t)stream>>>(
         x, n, hist_scale_dev, clip_outliers, (int)bins, hist);
     return (int)cudaGetLastError();
 }
@@ -420,7 +414,7 @@ int ppq_b200_histogram_c(const float *x, int64_t n, int64_t epc, int C, float hi
     const int64_t chunks = (epc + chunk - 1) / chunk;
     const int64_t items = rows * chunks;
     const int grid = (int)(items < (int64_t)kSMs * 8 ? items : (int64_t)kSMs * 8);
-    histogram_c_kernel<0><<<grid, kThreads, (size_t)bins * sizeof(int), (cudaStream_t)stream>>>(
+    histogram_c_kernel<0><<<grid, kThreads, (size_t)(bins + 1) * sizeof(int), (cudaStream_t)stream>>>(
         x, rows, epc, C, chunk, chunks, hist_scale, clip_outliers, (int)bins, hist);
     return (int)cudaGetLastError();
 }
@@ -445,7 +439,7 @@ int ppq_b200_multi_histogram_t(const ppq_b200_tensor_desc *descs, int count, int
     if (cpt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
     const int64_t items = (int64_t)count * cpt;
     const int grid = (int)(items < (int64_t)kSMs * 8 ? items : (int64_t)kSMs * 8);
-    multi_histogram_t_kernel<0><<<grid, kThreads, (size_t)bins * sizeof(int), (cudaStream_t)stream>>>(
+    multi_histogram_t_kernel<0><<<grid, kThreads, (size_t)(bins + 1) * sizeof(int), (cudaStream_t)stream>>>(
         descs, count, chunk, (int)cpt, hist_scale_arena, clip_outliers, (int)bins, hist_arena);
     return (int)cudaGetLastError();
 }

@@ -20,18 +20,23 @@ namespace ppqb {
 __device__ __forceinline__ double round_half_even(double v) { return rint(v); }
 
 // ppq_round_to_power_of_2 (utils/round.py:115-135): 2^round(log2(x)); ROUND_UP = ceil, ROUND_HALF_UP on the exponent.
+// ceil(log2 x) is taken from the binary exponent (exact, like Python's math.log2 on powers of two); the result is
+// built with ldexp, so no transcendental rounding can move it.
 __device__ __forceinline__ double pow2_round(double v, bool half_up) {
     if (v == 0.0) return 0.0;
     const double sign = v >= 0.0 ? 1.0 : -1.0;
-    const double l = log2(sign * v);
-    double e;
-    if (!half_up) e = ceil(l);
+    int e2;
+    const double m = frexp(sign * v, &e2);                             // |v| = m * 2^e2, m in [0.5, 1)
+    int e;
+    if (!half_up) e = (m == 0.5) ? e2 - 1 : e2;                        // ceil(log2 |v|)
     else {
         // Decimal ROUND_HALF_UP for positive exponents, ROUND_HALF_DOWN for negative ones (utils/round.py:80-82)
+        const double l = log2(sign * v);
         const double f = floor(l), frac = l - f;
-        if (frac > 0.5) e = f + 1.0; else if (frac < 0.5) e = f; else e = (l > 0.0) ? f + 1.0 : f;
+        if (m == 0.5) e = e2 - 1;                                       // exact power of two
+        else if (frac > 0.5) e = (int)f + 1; else if (frac < 0.5) e = (int)f; else e = (l > 0.0) ? (int)f + 1 : (int)f;
     }
-    return sign * exp2(e);
+    return sign * ldexp(1.0, e);
 }
 
 struct ScaleOffset { double scale, offset; };
@@ -153,8 +158,10 @@ kl_search_kernel(const int32_t *__restrict__ hist_arena, int bins, const float *
             float pv = h[i];
             if (i == br - 1) pv = __fadd_rn(pv, tail);
             const float p = __fdiv_rn(pv, total);
-            if (p == 0.f) continue;                                   // 0 * (finite) contributes exactly 0
-            const float q = h[i] > 0.f ? __fdiv_rn(gval[i / ratio], qsum) : 0.f;
+            // q = (spread value * non-empty mask) / sum: when every bin of the candidate is empty this is 0/0 = NaN upstream
+            // and the candidate's loss is NaN (python's sorted() then keeps that first candidate in front) -- keep that.
+            const float q = __fdiv_rn(h[i] > 0.f ? gval[i / ratio] : 0.f, qsum);
+            if (p == 0.f && q == q) continue;                         // 0 * (finite) contributes exactly 0
             kl += (double)p * (log10((double)p + 1e-30) - log10((double)q + 1e-30));
         }
         kl = block_sum(kl, scratch);

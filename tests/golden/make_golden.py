@@ -180,7 +180,7 @@ def gen_scalar_kats():
         lo, hi = sorted((float(np.float32(r.standard_normal() * 4)), float(np.float32(r.standard_normal() * 4))))
         if i % 9 == 0: lo = 0.0
         if i % 13 == 0: hi = lo  # degenerate range
-        if i % 11 == 0: lo, hi = abs(lo) + 0.1, abs(lo) + abs(hi) + 0.2   # strictly positive range
+        if i % 11 == 0: lo, hi = float(np.float32(abs(lo) + 0.1)), float(np.float32(abs(lo) + abs(hi) + 0.2))   # strictly positive range (fp32-representable: the observers hand fp32 min/max to this function)
         for sym in (True, False):
             for pow2 in (False, True):
                 for (qmin, qmax) in ((-128, 127), (0, 255), (-8, 7)):

@@ -255,8 +255,9 @@ def test_ft_matches_hardware_fp8_away_from_ties(ext):
     x = (torch.randn(1 << 20, device='cuda') * 10)
     y = ext.QuantizeTensor_FT(x, t1(1.0), t1(0.0), 4, 3, -448.0, 448.0, 0)
     hw = x.to(torch.float8_e4m3fn).float()
-    # differences are confined to exact ties (reference rule: ties toward zero) -- measure-zero for randn, so none here
-    assert torch.equal(y, hw)
+    # differences are confined to exact ties (reference rule: ties toward zero; ~1e-6 of fp32 values are exact E4M3 ties)
+    diff = y != hw
+    assert diff.sum().item() <= 16 and bool(((x[diff].view(torch.int32) & 0xFFFFF) == 0x80000).all())
 
 
 # ------------------------------------------------------------------------------------------------ collectors
@@ -388,20 +389,23 @@ def test_kl_search_kernel_vs_reference(ext):
             assert scale[i].item() == np.float32((want_best / 4096) * float(np.float32(c['hist_scale'])) * (4096 / qb)), c
 
 
-def test_observers_end_to_end_vs_reference(ext):
-    """Same data (seeded) through ppq_b200 observers on the GPU; scales/offsets must equal the reference CPU pipeline's
-    (tests/golden/observers.npz).  KL / MSE collect with the CUDA histogram semantics (x == max dropped) where the reference CPU
-    branch used torch.histc, so for those the selected scale is compared, not the histogram."""
+def test_observers_end_to_end_vs_reference(ext, oracle):
+    """Same data (seeded) through ppq_b200 observers on the GPU.
+    minmax (per tensor / per channel): scales and offsets must equal the reference CPU pipeline's (tests/golden/observers.npz).
+    kl / mse: the reference's CPU branch collects with torch.histc while its CUDA branch (and ours, bit-exact with its kernel:
+    test_gpu_vs_reference_cuda.py) floors |x|/hist_scale and drops x == max, so the expected scale is the oracle chain
+    device-histogram -> reference search; the CPU-path golden scale must still be within one search candidate."""
     from conftest import seeded_batches
     from ppq_b200 import LinearQuantizationConfig, QuantizationStates
     from ppq_b200.observer import Observer
     g = load_golden('observers.npz')
     for c in cases_of(g):
-        if c['algo'] == 'percentile': continue          # needs Quantile_T (CUDA index rule differs from the CPU kthvalue rule upstream)
+        if c['algo'] == 'percentile': continue          # Quantile_T path: covered in test_gpu_next_rows.py
         k, sym = c['k'], c['sym']
-        data = [dev(x) for x in seeded_batches(c['seed'], c['n'], tuple(c['shape']), c['relu'])]
-        cfg = LinearQuantizationConfig(symmetrical=sym, quant_min=-128 if sym else 0, quant_max=127 if sym else 255,
-                                       calibration=c['algo'], channel_axis=c.get('axis'))
+        host = seeded_batches(c['seed'], c['n'], tuple(c['shape']), c['relu'])
+        data = [dev(x) for x in host]
+        qmin, qmax = (-128, 127) if sym else (0, 255)
+        cfg = LinearQuantizationConfig(symmetrical=sym, quant_min=qmin, quant_max=qmax, calibration=c['algo'], channel_axis=c.get('axis'))
         ob = Observer(cfg)
         for x in data: ob.observe(x)
         ob.render_quantization_config()
@@ -409,8 +413,24 @@ def test_observers_end_to_end_vs_reference(ext):
             for x in data: ob.observe(x)
             ob.render_quantization_config()
         assert cfg.state == QuantizationStates.ACTIVATED
-        assert np.array_equal(cfg.scale.cpu().numpy().reshape(-1), g[f'scale{k}'].reshape(-1)), c
-        assert np.array_equal(cfg.offset.cpu().numpy().reshape(-1), g[f'offset{k}'].reshape(-1)), c
+        got_s, got_o = cfg.scale.cpu().numpy().reshape(-1), cfg.offset.cpu().numpy().reshape(-1)
+        if c['algo'] == 'minmax':
+            assert np.array_equal(got_s, g[f'scale{k}'].reshape(-1)), c
+            assert np.array_equal(got_o, g[f'offset{k}'].reshape(-1)), c
+            continue
+        vmin, vmax = (float(v) for v in g[f'minmax{k}'])
+        bins = 4096 if c['algo'] == 'kl' else 2048
+        hs = (max(abs(vmin), abs(vmax)) if sym else (vmax - vmin)) / bins
+        hist = np.zeros(bins, np.int32)
+        for x in host:
+            if sym: oracle.histogram_t(x, np.float32(hs), hist=hist)
+            else: oracle.histogram_asym_t(x, vmin, vmax, hist=hist)
+        assert np.array_equal(ob._hist.cpu().numpy(), hist), c
+        if c['algo'] == 'kl': want_s, want_o = oracle.kl_search(hist, hs, 8)
+        else: want_s, want_o = oracle.mse_search(hist, hs, vmin, qmin, qmax, sym)
+        assert got_s[0] == np.float32(want_s) and got_o[0] == np.float32(want_o), (c, got_s, want_s)
+        ref_s = float(g[f'scale{k}'].reshape(-1)[0])
+        assert abs(got_s[0] - ref_s) <= ref_s / 16, (c, got_s, ref_s)        # CPU-path (histc) scale: at most a candidate or two away
 
 
 # ------------------------------------------------------------------------------------------------ raw C ABI + full-size properties
@@ -447,7 +467,10 @@ def test_full_size_properties(ext):
         # FP8: idempotent, matches the hardware conversion away from ties
         f = ext.QuantizeTensor_FT(x, t1(1.0), t1(0.0), 4, 3, -448.0, 448.0, 0)
         assert torch.equal(ext.QuantizeTensor_FT(f, t1(1.0), t1(0.0), 4, 3, -448.0, 448.0, 0), f)
-        assert torch.equal(f, x.to(torch.float8_e4m3fn).float())
+        hw = x.to(torch.float8_e4m3fn).float()
+        diff = f != hw
+        # exact ties (low 20 mantissa bits == 0x80000: ~1e-6 of fp32 values) follow the reference rule (toward zero), hardware is ties-to-even
+        assert diff.sum().item() <= x.numel() * 4e-6 and bool(((x[diff].view(torch.int32) & 0xFFFFF) == 0x80000).all())
         # collectors: min/max equal torch's, histogram mass == number of in-range samples
         mm = torch.empty(2, device='cuda'); ext.MinMax_Init(mm[0:1], mm[1:2]); ext.MinMax_T(x, mm)
         assert mm[0].item() == x.min().item() and mm[1].item() == x.max().item()
