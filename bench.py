@@ -181,10 +181,16 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
     hist_events, mm_events, launches = [], [], [0]
 
+    from ppq_b200.calibration import MultiWeightQuantizer
+    wq = MultiWeightQuantizer(wl.w, wl.w_scale, wl.w_offset, channel_axis=0)
+
     def weights_pass():
-        for w, s, o in zip(wl.w, wl.w_scale, wl.w_offset):
-            ext.QuantizeTensor_LC(w, s, o, -128, 127, 0, 0)
-        launches[0] += len(wl.w)
+        if args.per_tensor_weight_launches:
+            for w, s, o in zip(wl.w, wl.w_scale, wl.w_offset): ext.QuantizeTensor_LC(w, s, o, -128, 127, 0, 0)
+            launches[0] += len(wl.w)
+        else:
+            wq()                                                  # all 54 weights, one launch
+            launches[0] += 1
 
     def calibrate(steps, timed):
         cal.reset()
@@ -358,6 +364,7 @@ def main():
     ap.add_argument('--rotate', type=int, default=4, help='distinct activation sets cycled through (each > L2)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--per-tensor-weight-launches', action='store_true', help='one QuantizeTensor_LC launch per weight (the reference flow) instead of the multi-tensor launch')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local_rank = int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':

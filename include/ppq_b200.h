@@ -63,6 +63,21 @@ PPQ_B200_API int ppq_b200_linear_quant_c_toint(const float *x, void *q, int out_
                                                const float *scale, const float *offset,
                                                int qmin, int qmax, int rounding, void *stream);
 
+/* Every per-channel weight of a network in ONE launch (the executor re-quantises all Conv/Gemm weights on every forward until
+ * they are baked: ppq/executor/torch.py:516-518; ParameterBakingPass, optim/baking.py:34-47).  Descriptors in DEVICE memory. */
+typedef struct {
+    const float *x;        /* fp32 weight                     */
+    float       *y;        /* fake-quantised output (!= x)    */
+    const float *scale;    /* [C] */
+    const float *offset;   /* [C] */
+    int64_t      n;        /* elements                        */
+    int64_t      epc;      /* elements per channel            */
+    int32_t      C;        /* channels                        */
+    int32_t      pad_;
+} ppq_b200_lc_desc;
+PPQ_B200_API int ppq_b200_multi_linear_quant_c(const ppq_b200_lc_desc *descs, int count, int64_t max_n,
+                                               int qmin, int qmax, int rounding, void *stream);
+
 /* ---- low-precision float fake-quant (FP8 E4M3 default; E in 1..5 and 2^(E-1)+M-2 in 0..30: E4M3, E5M2, E5M10 ...) --------------- */
 /* replaces QuantizeTensor_FT, ppq/csrc/cuda/floating.cu:36-75 with QuantizeScalarFloating,
  * common.cuh:154-226 (ffi.py:272-288 CUDA.FloatingQuantize_T).  Reference tie rule kept (ties toward zero in the

@@ -102,6 +102,16 @@ class ArenaCalibrator:
         self.launches += 1
 
     @torch.no_grad()
+    def observe_one(self, index: int, tensor: torch.Tensor):
+        """Immediate single-tensor collection into slot `index` (used while a forward is running: later in-place ops of the
+        network may overwrite the tensor, so it cannot wait for the end-of-forward multi-tensor launch)."""
+        if self.phase == 1:
+            self.ext.MinMax_T(tensor, self.minmax[index])
+        else:
+            self.ext.Histogram_T_DeviceScale(tensor, self.hist_scale[index:index + 1], True, self.hist[index])
+        self.launches += 1
+
+    @torch.no_grad()
     def end_phase(self):
         """Exchange + render of the finished phase.  Returns True when calibration is complete."""
         if self.phase == 1:
@@ -236,3 +246,34 @@ class RuntimeCalibrationPass:
             self.calibrate(dataloader, executor, hooks)
             self._reduce(2)
             for observer in self._observers.values(): observer.render_quantization_config()
+
+
+class MultiWeightQuantizer:
+    """All per-channel weights of a network fake-quantised by ONE launch (Multi_QuantizeTensor_LC).  The executor re-quantises
+    every Conv/Gemm weight on each forward until ParameterBakingPass freezes them (executor/torch.py:516-518); with ~54 small
+    tensors per ResNet-50 forward that is launch-latency, not bandwidth -- one descriptor table turns it into one kernel."""
+
+    def __init__(self, weights: Sequence[torch.Tensor], scales: Sequence[torch.Tensor], offsets: Sequence[torch.Tensor],
+                 channel_axis: int = 0, quant_min: int = -128, quant_max: int = 127, rounding: int = 0):
+        from .ffi import extension
+        self.ext = extension()
+        self.quant_min, self.quant_max, self.rounding = quant_min, quant_max, rounding
+        self.weights = [w.contiguous() for w in weights]
+        self.outputs = [torch.empty_like(w) for w in self.weights]
+        self.scales = [s.contiguous() for s in scales]
+        self.offsets = [o.contiguous() for o in offsets]
+        rows = []
+        for w, y, s, o in zip(self.weights, self.outputs, self.scales, self.offsets):
+            axis = channel_axis % w.dim()
+            epc = 1
+            for d in w.shape[axis + 1:]: epc *= int(d)
+            C = int(w.shape[axis])
+            assert s.numel() == C and o.numel() == C
+            rows.append([w.data_ptr(), y.data_ptr(), s.data_ptr(), o.data_ptr(), w.numel(), epc, C])
+        self.max_n = max(r[4] for r in rows)
+        self.descs = torch.tensor(rows, dtype=torch.int64).to(self.weights[0].device)
+
+    @torch.no_grad()
+    def __call__(self) -> List[torch.Tensor]:
+        self.ext.Multi_QuantizeTensor_LC(self.descs, self.max_n, self.quant_min, self.quant_max, self.rounding)
+        return self.outputs

@@ -70,15 +70,13 @@ __device__ __forceinline__ void stream_elements(const float *__restrict__ x, int
     if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
         const int64_t n4 = n >> 2;
         const float4 *x4 = reinterpret_cast<const float4 *>(x);
-        int64_t i = first;
-        for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
+        for (int64_t i = first; i < n4; i += kUnroll * stride) {      // kUnroll predicated loads in flight, also in the ragged round
             float4 v[kUnroll];
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) v[j] = ld_stream4(x4 + i + j * stride);
+            for (int j = 0; j < kUnroll; j++) if (i + j * stride < n4) v[j] = ld_stream4(x4 + i + j * stride);
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) { f(v[j].x); f(v[j].y); f(v[j].z); f(v[j].w); }
+            for (int j = 0; j < kUnroll; j++) if (i + j * stride < n4) { f(v[j].x); f(v[j].y); f(v[j].z); f(v[j].w); }
         }
-        for (; i < n4; i += stride) { const float4 v = ld_stream4(x4 + i); f(v.x); f(v.y); f(v.z); f(v.w); }
         const int64_t t = (n4 << 2) + first;
         if (t < n) f(x[t]);
     } else {
@@ -205,7 +203,7 @@ struct Counter {
 template <int VARIANT>
 __device__ __forceinline__ void hist_zero(int *sh, int bins) {
     if constexpr (VARIANT != 3) {
-        for (int i = threadIdx.x; i <= bins; i += kThreads) sh[i] = 0;      // + the trash slot
+        for (int i = threadIdx.x; i <= bins; i += blockDim.x) sh[i] = 0;    // + the trash slot
         __syncthreads();
     }
 }
@@ -213,7 +211,7 @@ template <int VARIANT>
 __device__ __forceinline__ void hist_flush(const int *sh, int bins, int32_t *gh) {
     if constexpr (VARIANT != 3) {
         __syncthreads();
-        for (int i = threadIdx.x; i < bins; i += kThreads) {
+        for (int i = threadIdx.x; i < bins; i += blockDim.x) {
             const int v = sh[i];
             if (v) atomicAdd(gh + i, v);
         }
@@ -223,7 +221,7 @@ __device__ __forceinline__ void hist_flush(const int *sh, int bins, int32_t *gh)
 
 // The ballot in VARIANT 0/2 needs all 32 lanes of a warp to call count() the same number of times: stream_elements
 // gives every lane of a warp the same trip count except in the ragged tail, so tails are padded with "drop" (-1).
-template <int VARIANT, class Bin>
+template <int VARIANT, class Bin, int U = kUnroll>
 __device__ __forceinline__ void hist_stream(const float *__restrict__ x, int64_t n, int64_t first, int64_t stride,
                                             const Bin &bin, Counter<VARIANT> &cnt) {
     if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
@@ -232,12 +230,12 @@ __device__ __forceinline__ void hist_stream(const float *__restrict__ x, int64_t
         const int64_t warp_first = first - (threadIdx.x & 31);              // lane 0 of this warp
         int64_t i = first;
         // full unrolled rounds: uniform across the warp because lanes are consecutive in i
-        for (; warp_first + (i - first) + 31 + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
-            float4 v[kUnroll];
+        for (; warp_first + (i - first) + 31 + (U - 1) * stride < n4; i += U * stride) {
+            float4 v[U];
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) v[j] = ld_stream4(x4 + i + j * stride);
+            for (int j = 0; j < U; j++) v[j] = ld_stream4(x4 + i + j * stride);
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) { const uint4 b = bin.bin4(v[j]); cnt.count(b.x); cnt.count(b.y); cnt.count(b.z); cnt.count(b.w); }
+            for (int j = 0; j < U; j++) { const uint4 b = bin.bin4(v[j]); cnt.count(b.x); cnt.count(b.y); cnt.count(b.z); cnt.count(b.w); }
         }
         // remaining rounds: warp-uniform loop bound, per-lane predicate
         for (; warp_first + (i - first) < n4; i += stride) {
@@ -256,49 +254,66 @@ __device__ __forceinline__ void hist_stream(const float *__restrict__ x, int64_t
     }
 }
 
-template <int VARIANT, class Bin>
-__global__ void __launch_bounds__(kThreads)
+constexpr int kHistThreads = 1024;   // one big CTA per SM: the flush of the private bins (bins global atomics per CTA) is what
+                                     // limits small-CTA configurations (measured: 256 thr x 8/SM 59 % -> 1024 thr x 1/SM 82 % of HBM peak)
+template <int VARIANT, class Bin, int U = kUnroll, int TPB = kHistThreads>
+__global__ void __launch_bounds__(TPB)
 histogram_kernel(const float *__restrict__ x, int64_t n, BinParams bp, int32_t *__restrict__ hist) {
     extern __shared__ int sh[];
     const int bins = bp.bins;
     hist_zero<VARIANT>(sh, bins);
     Counter<VARIANT> cnt(sh, hist, bins);
     const Bin bin(bp);
-    hist_stream<VARIANT>(x, n, (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads, bin, cnt);
+    hist_stream<VARIANT, Bin, U>(x, n, (int64_t)blockIdx.x * TPB + threadIdx.x, (int64_t)gridDim.x * TPB, bin, cnt);
     hist_flush<VARIANT>(sh, bins, hist);
 }
 
 // hist_scale read from device memory (phase 2 without a host round trip)
 template <int VARIANT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kHistThreads)
 histogram_dscale_kernel(const float *__restrict__ x, int64_t n, const float *__restrict__ hist_scale, int clip, int bins,
                         int32_t *__restrict__ hist) {
     extern __shared__ int sh[];
     hist_zero<VARIANT>(sh, bins);
     Counter<VARIANT> cnt(sh, hist, bins);
     const SymBin bin(__ldg(hist_scale), bins, clip != 0);
-    hist_stream<VARIANT>(x, n, (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads, bin, cnt);
+    hist_stream<VARIANT>(x, n, (int64_t)blockIdx.x * kHistThreads + threadIdx.x, (int64_t)gridDim.x * kHistThreads, bin, cnt);
     hist_flush<VARIANT>(sh, bins, hist);
 }
 
 template <int VARIANT>
-__global__ void __launch_bounds__(kThreads)
-multi_histogram_t_kernel(const ppq_b200_tensor_desc *__restrict__ descs, int count, int64_t chunk, int chunks_per_tensor,
+__global__ void __launch_bounds__(kHistThreads)
+multi_histogram_t_kernel(const ppq_b200_tensor_desc *__restrict__ descs, int count,
                          const float *__restrict__ hist_scale_arena, int clip, int bins, int32_t *__restrict__ hist_arena) {
+    // Each CTA owns one contiguous span of the concatenation of all tensors, so the private bins are zeroed / flushed
+    // (#CTAs + #tensors) times in total instead of once per fixed-size chunk.
     extern __shared__ int sh[];
-    const int64_t items = (int64_t)count * chunks_per_tensor;
-    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        const int t = (int)(item / chunks_per_tensor);
-        const int64_t c = item - (int64_t)t * chunks_per_tensor;
+    int64_t *prefix = reinterpret_cast<int64_t *>(sh + ((bins + 1 + 1) & ~1));       // [count + 1], 8-byte aligned
+    if (threadIdx.x == 0) {
+        int64_t run = 0;
+        for (int t = 0; t < count; t++) { prefix[t] = run; run += descs[t].n; }
+        prefix[count] = run;
+    }
+    __syncthreads();
+    const int64_t total = prefix[count];
+    int64_t span = (total + gridDim.x - 1) / gridDim.x;
+    span = (span + 3) & ~(int64_t)3;
+    const int64_t s0 = (int64_t)blockIdx.x * span, s1 = (s0 + span) < total ? (s0 + span) : total;
+    if (s0 >= total) return;
+    int t = 0;                                                         // first tensor overlapping [s0, s1): binary search
+    { int lo = 0, hi = count - 1; while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (prefix[mid] <= s0) lo = mid; else hi = mid - 1; } t = lo; }
+    for (; t < count && prefix[t] < s1; t++) {
         const ppq_b200_tensor_desc d = descs[t];
-        const int64_t begin = c * chunk;
-        if (begin >= d.n) continue;
-        const int64_t len = (d.n - begin) < chunk ? (d.n - begin) : chunk;
+        int64_t a = s0 - prefix[t]; if (a < 0) a = 0;
+        int64_t b = s1 - prefix[t]; if (b > d.n) b = d.n;
+        a = (a + 3) & ~(int64_t)3; if (a > d.n) a = d.n;               // both neighbours round the shared boundary the same way
+        if (b < d.n) b = (b + 3) & ~(int64_t)3; if (b > d.n) b = d.n;
+        if (b <= a) continue;                                          // uniform per CTA
         int32_t *gh = hist_arena + (int64_t)d.slot * bins;
         hist_zero<VARIANT>(sh, bins);
         Counter<VARIANT> cnt(sh, gh, bins);
         const SymBin bin(__ldg(hist_scale_arena + d.slot), bins, clip != 0);
-        hist_stream<VARIANT>(d.x + begin, len, threadIdx.x, kThreads, bin, cnt);
+        hist_stream<VARIANT>(d.x + a, b - a, threadIdx.x, kHistThreads, bin, cnt);
         hist_flush<VARIANT>(sh, bins, gh);
     }
 }
@@ -330,9 +345,9 @@ constexpr int kMaxSmemBins = 12287;            // (bins + 1) int32 slots within 
 
 // Elements each CTA should own before paying for zeroing + flushing `bins` counters.
 static inline int hist_grid(int64_t n, int bins) {
-    const int64_t per_cta = (int64_t)bins * 8 > 32768 ? (int64_t)bins * 8 : 32768;
+    const int64_t per_cta = (int64_t)bins * 16 > 65536 ? (int64_t)bins * 16 : 65536;
     int64_t g = (n + per_cta - 1) / per_cta;
-    const int64_t cap = (int64_t)kSMs * 8;
+    const int64_t cap = (int64_t)kSMs;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
@@ -345,10 +360,11 @@ static int launch_hist(const float *x, int64_t n, const BinParams &bin, int64_t 
     const int grid = var == 3 ? grid_for(n, kThreads, 16, 8) : hist_grid(n, (int)bins);
     const size_t smem = var == 3 ? 0 : (size_t)(bins + 1) * sizeof(int);
     switch (var) {
-    case 1:  histogram_kernel<1, Bin><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
-    case 2:  histogram_kernel<2, Bin><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
-    case 3:  histogram_kernel<3, Bin><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
-    default: histogram_kernel<0, Bin><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
+    case 1:  histogram_kernel<1, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
+    case 2:  histogram_kernel<2, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
+    case 3:  histogram_kernel<3, Bin, kUnroll, kThreads><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
+    case 4:  histogram_kernel<0, Bin, 8, kThreads><<<grid * 8 > kSMs * 8 ? kSMs * 8 : grid * 8, kThreads, smem, st>>>(x, n, bin, hist); break;   // the round-1 small-CTA layout
+    default: histogram_kernel<0, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     }
     return (int)cudaGetLastError();
 }
@@ -400,7 +416,7 @@ int ppq_b200_histogram_t_dscale(const float *x, int64_t n, const float *hist_sca
                                 int64_t bins, void *stream) {
     if (n <= 0 || !x || !hist || !hist_scale_dev || bins <= 0 || bins > kMaxSmemBins) return (int)cudaErrorInvalidValue;
     const int grid = hist_grid(n, (int)bins);
-    histogram_dscale_kernel<0><<<grid, kThreads, (size_t)(bins + 1) * sizeof(int), (cudaStream_t)stream>>>(
+    histogram_dscale_kernel<0><<<grid, kHistThreads, (size_t)(bins + 1) * sizeof(int), (cudaStream_t)stream>>>(
         x, n, hist_scale_dev, clip_outliers, (int)bins, hist);
     return (int)cudaGetLastError();
 }
@@ -432,15 +448,15 @@ int ppq_b200_multi_minmax_t(const ppq_b200_tensor_desc *descs, int count, int64_
 
 int ppq_b200_multi_histogram_t(const ppq_b200_tensor_desc *descs, int count, int64_t max_n, const float *hist_scale_arena,
                                int clip_outliers, int32_t *hist_arena, int64_t bins, void *stream) {
-    if (count <= 0 || max_n <= 0 || !descs || !hist_scale_arena || !hist_arena || bins <= 0 || bins > kMaxSmemBins)
-        return (int)cudaErrorInvalidValue;
-    const int64_t chunk = (int64_t)bins * 16 > 65536 ? (int64_t)bins * 16 : 65536;
-    const int64_t cpt = (max_n + chunk - 1) / chunk;
-    if (cpt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
-    const int64_t items = (int64_t)count * cpt;
-    const int grid = (int)(items < (int64_t)kSMs * 8 ? items : (int64_t)kSMs * 8);
-    multi_histogram_t_kernel<0><<<grid, kThreads, (size_t)(bins + 1) * sizeof(int), (cudaStream_t)stream>>>(
-        descs, count, chunk, (int)cpt, hist_scale_arena, clip_outliers, (int)bins, hist_arena);
+    if (count <= 0 || max_n <= 0 || !descs || !hist_scale_arena || !hist_arena || bins <= 0 || bins > kMaxSmemBins) return (int)cudaErrorInvalidValue;
+    const size_t smem = (size_t)((bins + 2) & ~1) * sizeof(int) + (size_t)(count + 1) * sizeof(int64_t);
+    if (smem > 48 * 1024) return (int)cudaErrorInvalidValue;
+    // grid: one CTA per SM, fewer when the whole job is small (each CTA should own >= 64 Ki elements before paying for a flush)
+    int64_t g = ((int64_t)count * max_n + 65535) / 65536;
+    if (g > kSMs) g = kSMs;
+    if (g < 1) g = 1;
+    multi_histogram_t_kernel<0><<<(int)g, kHistThreads, smem, (cudaStream_t)stream>>>(descs, count, hist_scale_arena, clip_outliers, (int)bins,
+                                                                                      hist_arena);
     return (int)cudaGetLastError();
 }
 

@@ -139,6 +139,19 @@ struct FastDiv {
     }
 };
 
+// 32-bit variant for indices < 2^31 (every tensor on this path has numel <= 2^31 - 1): IMAD.HI + IMAD + compare.
+struct FastDiv32 {
+    uint32_t magic, d;
+    __host__ __device__ FastDiv32() : magic(0), d(1) {}
+    __host__ __device__ explicit FastDiv32(uint32_t div) : magic(div <= 1 ? 0u : 0xFFFFFFFFu / div), d(div) {}
+    __device__ __forceinline__ uint32_t quot(uint32_t n) const {
+        if (d == 1) return n;
+        uint32_t q = __umulhi(n, magic);                            // floor(n/d) - 1 <= q <= floor(n/d) for n < 2^31
+        if (n - q * d >= d) ++q;
+        return q;
+    }
+};
+
 // ---- warp / block reductions ----------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll

@@ -45,25 +45,25 @@ constexpr int kUnroll = 4;          // independent 128-bit loads in flight per t
 
 // ---- per-tensor: one (scale, offset) for the whole tensor ---------------------------------------------------------------
 // VEC: x and y are 16-byte aligned -> float4 main loop + scalar tail; otherwise everything scalar.
+// Every round issues kUnroll predicated 128-bit loads before the first use, also in the ragged last round.
 template <class Op, class OutT, bool VEC>
 __global__ void __launch_bounds__(kThreads)
 ew_tensor_kernel(const float *__restrict__ x, OutT *__restrict__ y, int64_t n,
                  const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
-    const Op op(p, __ldg(scale), __ldg(offset));
+    const typename Op::Plan plan(p);
+    const Op op(plan, __ldg(scale), __ldg(offset));
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     if constexpr (VEC) {
         const int64_t n4 = n >> 2;
         const float4 *x4 = reinterpret_cast<const float4 *>(x);
-        int64_t i = tid;
-        for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
+        for (int64_t i = tid; i < n4; i += kUnroll * stride) {
             float4 v[kUnroll];
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) v[j] = ld_stream4(x4 + i + j * stride);
+            for (int j = 0; j < kUnroll; j++) if (i + j * stride < n4) v[j] = ld_stream4(x4 + i + j * stride);
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) Emit<Op, OutT>::vec(op, v[j], y, i + j * stride);
+            for (int j = 0; j < kUnroll; j++) if (i + j * stride < n4) Emit<Op, OutT>::vec(op, v[j], y, i + j * stride);
         }
-        for (; i < n4; i += stride) Emit<Op, OutT>::vec(op, ld_stream4(x4 + i), y, i);
         const int64_t t = (n4 << 2) + tid;                          // <= 3 leftover elements
         if (t < n) y[t] = Emit<Op, OutT>::one(op, x[t]);
     } else {
@@ -73,54 +73,118 @@ ew_tensor_kernel(const float *__restrict__ x, OutT *__restrict__ y, int64_t n,
 
 // ---- per-channel, vectorised: epc % 4 == 0 and 16-byte aligned bases, so a float4 never straddles a channel row ----------
 // Flat grid-stride over float4 vectors exactly like the per-tensor kernel (same memory-level parallelism); the channel of
-// vector vi is (vi / (epc/4)) % C, from two multiply-high divisions, and the operator (exact reciprocal, integer offset)
-// is rebuilt per vector: ~9 extra issue slots per element, still under the HBM-bound budget.
+// vector vi is (vi / (epc/4)) % C, from two 32-bit multiply-high divisions (numel < 2^31 is part of the contract), and the
+// operator (exact reciprocal, integer offset) is rebuilt per vector.
 template <class Op, class OutT>
-__global__ void __launch_bounds__(kThreads)
-ew_channel_vec_kernel(const float *__restrict__ x, OutT *__restrict__ y, int64_t n4, int C,
-                      FastDiv div_epc4, FastDiv div_C,
-                      const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
+__device__ __forceinline__ void channel_vec_body(const float *__restrict__ x, OutT *__restrict__ y, uint32_t n4, int C,
+                                                 const FastDiv32 &div_epc4, const FastDiv32 &div_C,
+                                                 const float *__restrict__ scale, const float *__restrict__ offset,
+                                                 const typename Op::Plan &plan, uint32_t first, uint32_t stride) {
     const float4 *x4 = reinterpret_cast<const float4 *>(x);
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    auto emit = [&](const float4 &v, int64_t vi) {
-        const int64_t row = (int64_t)div_epc4.quot((uint64_t)vi);
-        const int c = (int)(row - (int64_t)div_C.quot((uint64_t)row) * C);
-        const Op op(p, __ldg(scale + c), __ldg(offset + c));
-        Emit<Op, OutT>::vec(op, v, y, vi);
-    };
-    for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
+    for (uint64_t i = first; i < n4; i += (uint64_t)kUnroll * stride) {
         float4 v[kUnroll];
 #pragma unroll
-        for (int j = 0; j < kUnroll; j++) v[j] = ld_stream4(x4 + i + j * stride);
+        for (int j = 0; j < kUnroll; j++) if (i + (uint64_t)j * stride < n4) v[j] = ld_stream4(x4 + i + (uint64_t)j * stride);
 #pragma unroll
-        for (int j = 0; j < kUnroll; j++) emit(v[j], i + j * stride);
+        for (int j = 0; j < kUnroll; j++) {
+            const uint64_t vi = i + (uint64_t)j * stride;
+            if (vi < n4) {
+                const uint32_t row = div_epc4.quot((uint32_t)vi);
+                const uint32_t c = row - div_C.quot(row) * (uint32_t)C;
+                const Op op(plan, __ldg(scale + c), __ldg(offset + c));
+                Emit<Op, OutT>::vec(op, v[j], y, (int64_t)vi);
+            }
+        }
     }
-    for (; i < n4; i += stride) emit(ld_stream4(x4 + i), i);
+}
+
+template <class Op, class OutT>
+__global__ void __launch_bounds__(kThreads)
+ew_channel_vec_kernel(const float *__restrict__ x, OutT *__restrict__ y, uint32_t n4, int C,
+                      FastDiv32 div_epc4, FastDiv32 div_C,
+                      const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
+    const typename Op::Plan plan(p);
+    channel_vec_body<Op, OutT>(x, y, n4, C, div_epc4, div_C, scale, offset, plan, blockIdx.x * kThreads + threadIdx.x, gridDim.x * kThreads);
 }
 
 // ---- per-channel, generic: any epc (1, 9, 27, ...), any alignment ---------------------------------------------------------
 // Each thread owns 4 consecutive elements; (row, col) of the first comes from one fast division, the rest by walking.
 template <class Op, class OutT>
-__global__ void __launch_bounds__(kThreads)
-ew_channel_generic_kernel(const float *__restrict__ x, OutT *__restrict__ y, int64_t n, int64_t epc, int C,
-                          FastDiv div_epc, FastDiv div_C,
-                          const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
+__device__ __forceinline__ void channel_generic_body(const float *__restrict__ x, OutT *__restrict__ y, int64_t n, int64_t epc, int C,
+                                                     const FastDiv &div_epc, const FastDiv &div_C,
+                                                     const float *__restrict__ scale, const float *__restrict__ offset,
+                                                     const typename Op::Plan &plan, int64_t first, int64_t stride) {
     const int64_t groups = (n + 3) >> 2;
-    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < groups; g += (int64_t)gridDim.x * kThreads) {
+    for (int64_t g = first; g < groups; g += stride) {
         const int64_t e0 = g << 2;
         int64_t row = (int64_t)div_epc.quot((uint64_t)e0);
         int64_t col = e0 - row * epc;
         int c = (int)(row - (int64_t)div_C.quot((uint64_t)row) * C);
         const int cnt = (int)((n - e0) < 4 ? (n - e0) : 4);
         if (col + cnt <= epc) {                                      // all in one row: one operator for the group
-            const Op op(p, __ldg(scale + c), __ldg(offset + c));
+            const Op op(plan, __ldg(scale + c), __ldg(offset + c));
             for (int j = 0; j < cnt; j++) y[e0 + j] = Emit<Op, OutT>::one(op, ld_stream1(x + e0 + j));
         } else {
             for (int j = 0; j < cnt; j++) {
-                const Op op(p, __ldg(scale + c), __ldg(offset + c));
+                const Op op(plan, __ldg(scale + c), __ldg(offset + c));
                 y[e0 + j] = Emit<Op, OutT>::one(op, ld_stream1(x + e0 + j));
                 if (++col == epc) { col = 0; if (++c == C) c = 0; }
+            }
+        }
+    }
+}
+
+template <class Op, class OutT>
+__global__ void __launch_bounds__(kThreads)
+ew_channel_generic_kernel(const float *__restrict__ x, OutT *__restrict__ y, int64_t n, int64_t epc, int C,
+                          FastDiv div_epc, FastDiv div_C,
+                          const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
+    const typename Op::Plan plan(p);
+    channel_generic_body<Op, OutT>(x, y, n, epc, C, div_epc, div_C, scale, offset, plan,
+                                   (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads);
+}
+
+// ---- multi-tensor per-channel fake-quant: every Conv/Gemm weight of a network in ONE launch ------------------------------------
+// Work item = (tensor, chunk of kMultiChunk elements); the per-tensor geometry (epc, C, fast-division constants) lives in the
+// descriptor table in device memory.
+constexpr int64_t kMultiChunk = 16384;
+template <class Op>
+__global__ void __launch_bounds__(kThreads)
+multi_channel_kernel(const ppq_b200_lc_desc *__restrict__ descs, int count, int chunks_per_tensor, typename Op::Params p) {
+    const typename Op::Plan plan(p);
+    const int64_t items = (int64_t)count * chunks_per_tensor;
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int t = (int)(item / chunks_per_tensor);
+        const int64_t ck = item - (int64_t)t * chunks_per_tensor;
+        const ppq_b200_lc_desc d = descs[t];
+        const int64_t begin = ck * kMultiChunk;
+        if (begin >= d.n) continue;
+        const int64_t len = (d.n - begin) < kMultiChunk ? (d.n - begin) : kMultiChunk;
+        // chunk boundaries are multiples of 4 elements, so group/vector alignment inside a chunk equals that of the tensor
+        const bool vec = (d.epc % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.x) | reinterpret_cast<uintptr_t>(d.y)) & 15u) == 0;
+        if (vec) {
+            const uint32_t v0 = (uint32_t)(begin >> 2), v1 = (uint32_t)((begin + len) >> 2);
+            const FastDiv32 de((uint32_t)(d.epc >> 2)), dc((uint32_t)d.C);
+            const float4 *x4 = reinterpret_cast<const float4 *>(d.x);
+            for (uint32_t vi = v0 + threadIdx.x; vi < v1; vi += kThreads) {
+                const uint32_t row = de.quot(vi);
+                const uint32_t c = row - dc.quot(row) * (uint32_t)d.C;
+                const Op op(plan, __ldg(d.scale + c), __ldg(d.offset + c));
+                Emit<Op, float>::vec(op, ld_stream4(x4 + vi), d.y, (int64_t)vi);
+            }
+        } else {
+            // generic walk restricted to [begin, begin + len)
+            const FastDiv32 de((uint32_t)d.epc), dc((uint32_t)d.C);
+            for (int64_t e0 = begin + 4 * (int64_t)threadIdx.x; e0 < begin + len; e0 += 4 * kThreads) {
+                const uint32_t row = de.quot((uint32_t)e0);
+                int64_t col = e0 - (int64_t)row * d.epc;
+                int c = (int)(row - dc.quot(row) * (uint32_t)d.C);
+                const int cnt = (int)((begin + len - e0) < 4 ? (begin + len - e0) : 4);
+                for (int j = 0; j < cnt; j++) {
+                    const Op op(plan, __ldg(d.scale + c), __ldg(d.offset + c));
+                    d.y[e0 + j] = op.apply(ld_stream1(d.x + e0 + j));
+                    if (++col == d.epc) { col = 0; if (++c == d.C) c = 0; }
+                }
             }
         }
     }
@@ -137,7 +201,7 @@ static int launch_tensor(const float *x, OutT *y, int64_t n, const float *scale,
                          typename Op::Params p, cudaStream_t st) {
     if (n <= 0 || !x || !y || !scale || !offset) return (int)cudaErrorInvalidValue;
     const bool vec = aligned16(x) && out_aligned<OutT>(y);
-    const int grid = grid_for(vec ? (n + 3) / 4 : n, kThreads, vec ? kUnroll : 4, 8);
+    const int grid = grid_for(vec ? (n + 3) / 4 : n, kThreads, vec ? kUnroll : 4, 16);
     if (vec) ew_tensor_kernel<Op, OutT, true><<<grid, kThreads, 0, st>>>(x, y, n, scale, offset, p);
     else     ew_tensor_kernel<Op, OutT, false><<<grid, kThreads, 0, st>>>(x, y, n, scale, offset, p);
     return (int)cudaGetLastError();
@@ -150,10 +214,12 @@ static int launch_channel(const float *x, OutT *y, int64_t n, int64_t epc, int C
     if (epc > 0x7fffffffLL || n % epc != 0) return (int)cudaErrorInvalidValue;
     if (epc % 4 == 0 && aligned16(x) && out_aligned<OutT>(y)) {
         const int64_t n4 = n / 4;
-        const int grid = grid_for(n4, kThreads, kUnroll, 8);
-        ew_channel_vec_kernel<Op, OutT><<<grid, kThreads, 0, st>>>(x, y, n4, C, FastDiv((uint32_t)(epc / 4)), FastDiv((uint32_t)C),
-                                                                      scale, offset, p);
-        return (int)cudaGetLastError();
+        if (n4 <= 0x7fffffffLL) {
+            const int grid = grid_for(n4, kThreads, kUnroll, 16);
+            ew_channel_vec_kernel<Op, OutT><<<grid, kThreads, 0, st>>>(x, y, (uint32_t)n4, C, FastDiv32((uint32_t)(epc / 4)), FastDiv32((uint32_t)C),
+                                                                          scale, offset, p);
+            return (int)cudaGetLastError();
+        }
     }
     const int grid = grid_for((n + 3) / 4, kThreads, 1, 8);
     ew_channel_generic_kernel<Op, OutT><<<grid, kThreads, 0, st>>>(x, y, n, epc, C, FastDiv((uint32_t)epc), FastDiv((uint32_t)C),
@@ -218,6 +284,17 @@ int ppq_b200_linear_quant_c_toint(const float *x, void *q, int out_bits, int64_t
     if (!toint_bits_ok(out_bits)) return (int)cudaErrorInvalidValue;
     if (out_bits == 8) return launch_channel<LinearOp<-1>, int8_t>(x, (int8_t *)q, n, epc, C, scale, offset, {qmin, qmax, rounding}, st);
     return launch_channel<LinearOp<-1>, int32_t>(x, (int32_t *)q, n, epc, C, scale, offset, {qmin, qmax, rounding}, st);
+}
+
+int ppq_b200_multi_linear_quant_c(const ppq_b200_lc_desc *descs, int count, int64_t max_n, int qmin, int qmax, int rounding, void *stream) {
+    if (count <= 0 || max_n <= 0 || !descs || qmin > qmax) return (int)cudaErrorInvalidValue;
+    const int64_t cpt = (max_n + kMultiChunk - 1) / kMultiChunk;
+    if (cpt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+    const int64_t items = (int64_t)count * cpt;
+    const int grid = (int)(items < (int64_t)kSMs * 16 ? items : (int64_t)kSMs * 16);
+    if (rounding == RND_HALF_EVEN) multi_channel_kernel<LinearOp<0>><<<grid, kThreads, 0, (cudaStream_t)stream>>>(descs, count, (int)cpt, {qmin, qmax, 0});
+    else multi_channel_kernel<LinearOp<-1>><<<grid, kThreads, 0, (cudaStream_t)stream>>>(descs, count, (int)cpt, {qmin, qmax, rounding});
+    return (int)cudaGetLastError();
 }
 
 int ppq_b200_float_quant_t(const float *x, float *y, int64_t n, const float *scale, const float *offset,

@@ -101,7 +101,8 @@ linear_quant_t_tma_kernel(const float *__restrict__ x, float *__restrict__ y, in
         }
     } else {
         // ---------------- consumers ----------------
-        const LinearOp<0> op({lo, hi, 0}, __ldg(scale), __ldg(offset));
+        const LinearOp<0>::Plan plan(LinearOp<0>::Params{lo, hi, 0});
+        const LinearOp<0> op(plan, __ldg(scale), __ldg(offset));
         for (int64_t k = 0; k < my_tiles; k++) {
             const int s = (int)(k % kStages);
             const uint32_t ph = (uint32_t)((k / kStages) & 1);

@@ -2,6 +2,8 @@
 // train.cu).  LinearOp == QuantizeScalar + DequantizeScalar (/root/reference/ppq/csrc/cuda/common.cuh:116-147),
 // FloatOp == QuantizeScalarFloating (common.cuh:154-226) followed by the float dequantise of floating.cu:50-53.
 //
+// Structure: Params (host, by value) -> Plan (device, once per thread: everything that depends only on the format /
+// clip range) -> Op (device, once per tensor or per channel row: the scale's exact reciprocal, the offset).
 // Every operator has a scalar form and a 4-wide form.  The 4-wide form computes the four exact quotients as one
 // straight-line block (four independent 5-deep FMA chains the scheduler can interleave) and tests them for the rare
 // "needs the IEEE slow path" condition once per vector instead of once per element.
@@ -10,12 +12,19 @@
 
 namespace ppqb {
 
+__device__ __forceinline__ float fmin_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
 // MODE >= 0: compile-time rounding mode; MODE == -1: run-time mode (uniform switch).
 template <int MODE>
 struct LinearOp {
     struct Params { int lo, hi, mode; };
+    struct Plan {
+        int lo, hi, mode;
+        __device__ __forceinline__ explicit Plan(const Params &p) : lo(p.lo), hi(p.hi), mode(p.mode) {}
+    };
     ExactDiv d; int o, lo, hi, mode;
-    __device__ __forceinline__ LinearOp(const Params &p, float s, float off) : lo(p.lo), hi(p.hi), mode(p.mode) {
+    __device__ __forceinline__ LinearOp(const Plan &p, float s, float off) : lo(p.lo), hi(p.hi), mode(p.mode) {
         d.init(s);
         o = offset_to_int(off);
     }
@@ -40,48 +49,69 @@ struct LinearOp {
 template <int MODE>
 struct FloatOp {
     struct Params { int E, M, mode; float cmin, cmax; };
-    ExactDiv d; float off, hi, lo, cmin, cmax, min_sub, inv_min_sub;
-    uint32_t sub_thresh_bits, half_minus1, keep_mask; int M, mode;
-    __device__ __forceinline__ FloatOp(const Params &p, float s, float o) : off(o), cmin(p.cmin), cmax(p.cmax), M(p.M), mode(p.mode) {
-        d.init(s);
-        const int emin = -(1 << (p.E - 1)) + 1, emax = 1 << (p.E - 1);
-        const uint32_t top = ~(0x007FFFFFu >> p.M) & 0x007FFFFFu;
-        const float tmax = __uint_as_float((uint32_t)((emax + 127) << 23) + top);   // E4M3: 480
-        hi = fminf(p.cmax, tmax);
-        lo = fmaxf(p.cmin, -tmax);
-        const int k = (1 << (p.E - 1)) + p.M - 2;                                   // min subnormal = 2^-k
-        min_sub = __uint_as_float((uint32_t)(127 - k) << 23);
-        inv_min_sub = __uint_as_float((uint32_t)(127 + k) << 23);                   // u / 2^-k == u * 2^k exactly
-        sub_thresh_bits = (uint32_t)(emin + 1 + 127) << 23;                         // |u| < 2^(emin+1) -> subnormal grid
-        half_minus1 = (1u << (22 - p.M)) - 1u;
-        keep_mask = ~((1u << (23 - p.M)) - 1u);
-    }
-    static constexpr float kDivLimit = 1.15e18f;                                    // ~2^60: beyond this use div.rn
-    // u = x / s already computed exactly
+    struct Plan {
+        float hi, lo, cmin, cmax, min_sub, inv_min_sub, sub_magic;
+        uint32_t sub_thresh_bits, half_minus1, keep_mask; int M, mode; bool fast;
+        __device__ __forceinline__ explicit Plan(const Params &p) : cmin(p.cmin), cmax(p.cmax), M(p.M), mode(p.mode) {
+            const int emin = -(1 << (p.E - 1)) + 1, emax = 1 << (p.E - 1);
+            const uint32_t top = ~(0x007FFFFFu >> p.M) & 0x007FFFFFu;
+            const float tmax = __uint_as_float((uint32_t)((emax + 127) << 23) + top);   // E4M3: 480
+            hi = fminf(p.cmax, tmax);
+            lo = fmaxf(p.cmin, -tmax);
+            const int k = (1 << (p.E - 1)) + p.M - 2;                                   // min subnormal = 2^-k
+            min_sub = __uint_as_float((uint32_t)(127 - k) << 23);
+            inv_min_sub = __uint_as_float((uint32_t)(127 + k) << 23);                   // u / 2^-k == u * 2^k exactly
+            sub_magic = __uint_as_float(((uint32_t)(127 + 23 - k) << 23) | 0x00400000u);  // 1.5 * 2^(23-k): ulp == 2^-k
+            sub_thresh_bits = (uint32_t)(emin + 1 + 127) << 23;                         // |u| < 2^(emin+1) -> subnormal grid
+            half_minus1 = (1u << (22 - p.M)) - 1u;
+            keep_mask = ~((1u << (23 - p.M)) - 1u);
+            // Branch-free fast path (HALF_EVEN only): valid when both saturation bounds are fixed points of the rounding, i.e.
+            // lie on the FP(E,M) grid, so that round(clamp(u)) == the reference's early returns and its final CLIP is a no-op.
+            const uint32_t hb = __float_as_uint(hi) & 0x7FFFFFFFu, lb = __float_as_uint(lo) & 0x7FFFFFFFu;
+            fast = (hi > 0.f) && (lo < 0.f) && hb >= sub_thresh_bits && lb >= sub_thresh_bits &&
+                   (((hb + half_minus1) & keep_mask) == hb) && (((lb + half_minus1) & keep_mask) == lb) && hi <= p.cmax && lo >= p.cmin;
+        }
+    };
+    const Plan &pl; ExactDiv d; float off;
+    __device__ __forceinline__ FloatOp(const Plan &p, float s, float o) : pl(p), off(o) { d.init(s); }
+    static constexpr float kDivLimit = 1.15e18f;                                        // ~2^60: beyond this use div.rn
+    // u = x / s already computed exactly; returns the value on the FP(E,M) grid
     __device__ __forceinline__ float grid(float u) const {
-        if (u > hi) return hi;
-        if (u < lo) return lo;
+        if constexpr (MODE == RND_HALF_EVEN) {
+            if (pl.fast) {
+                const float uc = fmin_nan(fmax_nan(u, pl.lo), pl.hi);                   // NaN stays NaN (canonical), like the comparisons upstream
+                const uint32_t b = __float_as_uint(uc), mag = b & 0x7FFFFFFFu;
+                // normal range: round the magnitude's discarded mantissa bits half-DOWN (an exact tie keeps the lower value,
+                // because rint(0.5) == 0 upstream); the carry may bump the exponent
+                const uint32_t nb = ((mag + pl.half_minus1) & pl.keep_mask) + (b & 0x80000000u);
+                // subnormal range: ties-to-even on the 2^-k grid, computed with the add-magic-constant trick (sign of zero lost,
+                // exactly like the int round trip upstream)
+                const float sub = __fsub_rn(__fadd_rn(uc, pl.sub_magic), pl.sub_magic);
+                return mag < pl.sub_thresh_bits ? sub : __uint_as_float(nb);
+            }
+        }
+        if (u > pl.hi) return pl.hi;
+        if (u < pl.lo) return pl.lo;
         const uint32_t b = __float_as_uint(u);
         const uint32_t sign = b & 0x80000000u, mag = b & 0x7FFFFFFFu;
-        if (mag < sub_thresh_bits) {
+        if (mag < pl.sub_thresh_bits) {
             int r;
-            const float v = __fmul_rn(u, inv_min_sub);
-            if constexpr (MODE >= 0) r = round2int<MODE>(v); else r = round2int_dyn(v, mode);
-            return __fmul_rn(__int2float_rn(r), min_sub);
+            const float v = __fmul_rn(u, pl.inv_min_sub);
+            if constexpr (MODE >= 0) r = round2int<MODE>(v); else r = round2int_dyn(v, pl.mode);
+            return __fmul_rn(__int2float_rn(r), pl.min_sub);
         }
         uint32_t rb;
         if constexpr (MODE == RND_HALF_EVEN) {
-            // rint(frac) with frac in [0,1): 1 iff the discarded bits exceed one half (an exact tie gives 0)
-            rb = ((mag + half_minus1) & keep_mask) + sign;
+            rb = ((mag + pl.half_minus1) & pl.keep_mask) + sign;
         } else {
             const uint32_t mant = b & 0x007FFFFFu;
-            const float frac = __fsub_rn(__uint_as_float(((mant << M) & 0x007FFFFFu) + 0x3F800000u), 1.0f);
+            const float frac = __fsub_rn(__uint_as_float(((mant << pl.M) & 0x007FFFFFu) + 0x3F800000u), 1.0f);
             int r;
-            if constexpr (MODE >= 0) r = round2int<MODE>(frac); else r = round2int_dyn(frac, mode);
-            rb = sign + (((mant >> (23 - M)) + (uint32_t)r) << (23 - M)) + (b & 0x7F800000u);
+            if constexpr (MODE >= 0) r = round2int<MODE>(frac); else r = round2int_dyn(frac, pl.mode);
+            rb = sign + (((mant >> (23 - pl.M)) + (uint32_t)r) << (23 - pl.M)) + (b & 0x7F800000u);
         }
         const float q = __uint_as_float(rb);
-        return q > cmax ? cmax : (q < cmin ? cmin : q);
+        return q > pl.cmax ? pl.cmax : (q < pl.cmin ? pl.cmin : q);
     }
     __device__ __forceinline__ float dequant(float q) const { return __fmul_rn(__fsub_rn(q, off), d.s); }
     __device__ __forceinline__ float apply(float x) const { return dequant(grid(d.div(x, kDivLimit))); }

@@ -264,6 +264,14 @@ std::vector<Tensor> KL_Search(const Tensor &hist_arena, const int64_t bins, cons
                                    scale.data_ptr<float>(), best.data_ptr<int>(), Stream()), "KL_Search");
     return {scale, best};
 }
+// descs: int64 tensor [count, 7] on the device = (x, y, scale, offset, numel, epc, C) -- bit-compatible with ppq_b200_lc_desc
+void Multi_QuantizeTensor_LC(const Tensor &descs, const int64_t max_numel, const int clip_min, const int clip_max, const int rounding) {
+    CheckTensor(descs, at::kLong, "Descriptors(Expect to be INT64)");
+    if (descs.dim() != 2 || descs.size(1) != 7 || !descs.is_contiguous()) throw KernelFailure("Kernel Failure, descriptor table must be [count, 7] int64.");
+    const c10::cuda::CUDAGuard guard(descs.device());
+    CheckStatus(ppq_b200_multi_linear_quant_c(reinterpret_cast<const ppq_b200_lc_desc *>(descs.data_ptr<int64_t>()), (int)descs.size(0), max_numel,
+                                              clip_min, clip_max, rounding, Stream()), "Multi_QuantizeTensor_LC");
+}
 int set_variant(const std::string &kernel, int variant) { return ppq_b200_set_variant(kernel.c_str(), variant); }
 int get_variant(const std::string &kernel) { return ppq_b200_get_variant(kernel.c_str()); }
 
@@ -285,6 +293,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     register_more(m);
     // B200-native extras
     m.def("QuantizeTensor_toInt", QuantizeTensor_toInt, "QuantizeTensor_toInt");
+    m.def("Multi_QuantizeTensor_LC", Multi_QuantizeTensor_LC, "Multi_QuantizeTensor_LC");
     m.def("MinMax_Init", MinMax_Init, "MinMax_Init");
     m.def("MinMax_T", MinMax_T, "MinMax_T");
     m.def("MinMax_C", MinMax_C, "MinMax_C");

@@ -1,0 +1,264 @@
+"""Executor: the slice of TorchExecutor that the hot path lives in (/root/reference/ppq/executor/torch.py:457-577, 610-652)
+for a torch.nn.Module network -- no graph IR, no ONNX (neither is part of the path).
+
+What is mirrored, with the reference's semantics:
+  * every quantable operation (a Conv2d / Linear / ReLU / pooling call site) owns TensorQuantizationConfigs for its inputs,
+    parameters and outputs with the TensorRT-INT8 policy of ppq/quantization/quantizer/TensorRTQuantizer.py:12-105:
+    per-tensor symmetric INT8 activations, per-channel symmetric INT8 weights on axis 0 ('minmax'), bias FP32;
+  * forward(inputs, hooks): for each operation call quantize_function on every input and parameter (weights are re-quantised
+    on EVERY forward until baked: torch.py:516-518), run pre-forward hooks with (fp32, quantised) values, run the op, quantise
+    the outputs, run post-forward hooks (torch.py:526-553).  Only ACTIVATED / PASSIVE configs quantise (core/quant.py:357-359);
+  * Conv -> ReLU fusion marks the conv output OVERLAPPED (QuantizeFusionPass) so it is neither observed nor
+    quantised; downstream inputs are dominated by the producer's output config;
+  * dummy_forward-style ParameterQuantizePass (optim/parameters.py:172-215): per-channel min/max + scale search for weights.
+Conv / Gemm execution itself stays in torch (cuDNN / cuBLAS), as in the reference.
+
+B200-native addition: `collect=True` makes the executor hand the observed fp32 tensors of a whole forward to an ArenaCalibrator
+(one multi-tensor launch per phase) instead of firing one observer launch per tensor.
+"""
+from typing import Dict, List, Optional
+
+import torch
+
+from .core import LinearQuantizationConfig, QuantizationStates, TensorQuantizationConfig
+from .qfunction import PPQuantFunction
+
+_KINDS = {torch.nn.Conv2d: 'Conv', torch.nn.Linear: 'Gemm', torch.nn.ReLU: 'Relu', torch.nn.ReLU6: 'Clip',
+          torch.nn.MaxPool2d: 'MaxPool', torch.nn.AdaptiveAvgPool2d: 'GlobalAveragePool', torch.nn.AvgPool2d: 'AveragePool'}
+
+
+def fuse_conv_bn(model: torch.nn.Module) -> torch.nn.Module:
+    """PPQ folds BatchNorm into the preceding convolution when it loads a graph (core/common.py:41 FORMATTER_FUSE_BN)."""
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    model.eval()
+
+    def walk(mod):
+        prev_name, prev = None, None
+        for name, child in list(mod.named_children()):
+            if isinstance(child, torch.nn.BatchNorm2d) and isinstance(prev, torch.nn.Conv2d):
+                setattr(mod, prev_name, fuse_conv_bn_eval(prev, child))
+                setattr(mod, name, torch.nn.Identity())
+                prev_name, prev = None, None
+                continue
+            walk(child)
+            prev_name, prev = name, child
+    walk(model)
+    return model
+
+
+class QuantableOperation:
+    """One call site of a quantable module.  `input_configs()` / `output_configs()` are what OperationObserver walks
+    (observer/__init__.py:92-113)."""
+
+    def __init__(self, name: str, module: torch.nn.Module, kind: str, is_graph_input: bool):
+        self.name, self.module, self.kind = name, module, kind
+        act = dict(symmetrical=True, quant_min=-128, quant_max=127, calibration='percentile')
+        self.input_cfg: Optional[TensorQuantizationConfig] = LinearQuantizationConfig(**act) if is_graph_input else None
+        self.weight_cfg: Optional[TensorQuantizationConfig] = None
+        if kind in ('Conv', 'Gemm'):
+            self.weight_cfg = LinearQuantizationConfig(symmetrical=True, quant_min=-128, quant_max=127, channel_axis=0, calibration='minmax')
+        self.output_cfg: TensorQuantizationConfig = LinearQuantizationConfig(**act)
+
+    def input_configs(self):
+        if self.input_cfg is not None: yield (self.name + ':in', self.input_cfg, False)
+        if self.weight_cfg is not None: yield (self.name + ':weight', self.weight_cfg, True)
+
+    def output_configs(self):
+        yield (self.name + ':out', self.output_cfg)
+
+
+class TorchExecutor:
+    def __init__(self, model: torch.nn.Module, example_input: torch.Tensor, fuse_bn: bool = True):
+        self.model = fuse_conv_bn(model) if fuse_bn else model.eval()
+        self.operations: Dict[str, QuantableOperation] = {}
+        self._order: List[str] = []
+        self._calls: Dict[int, int] = {}
+        self._names = {id(m): n for n, m in self.model.named_modules()}
+        self._hooks, self._collect, self._collected, self._sink = None, False, None, None
+        self._tracing, self._last_out = True, None
+        self._quant_fn = PPQuantFunction
+        for m in self.model.modules():
+            if type(m) in _KINDS:
+                m.register_forward_pre_hook(self._pre)
+                m.register_forward_hook(self._post)
+        with torch.no_grad():
+            self._begin()
+            self.model(example_input)
+        self._tracing = False
+
+    # -- graph view used by the calibration pass
+    def quantable_operations(self):
+        return [(n, self.operations[n]) for n in self._order]
+
+    def quantize_function(self, tensor: torch.Tensor, config: Optional[TensorQuantizationConfig]) -> torch.Tensor:
+        """torch.py:610-613."""
+        if config is None or not QuantizationStates.is_activated(config.state): return tensor
+        return self._quant_fn(tensor, config)
+
+    def _begin(self):
+        self._calls.clear()
+        self._collected = []
+
+    def _op_of(self, module) -> QuantableOperation:
+        idx = self._calls.get(id(module), 0)
+        name = f'{self._names[id(module)]}#{idx}'
+        if self._tracing and name not in self.operations:
+            self.operations[name] = QuantableOperation(name, module, _KINDS[type(module)], is_graph_input=(len(self._order) == 0))
+            self._order.append(name)
+        return self.operations[name]
+
+    def _pre(self, module, args):
+        op = self._op_of(module)
+        x = args[0]
+        if self._tracing:
+            # conv -> relu fusion: the activation takes over the producer's output config (QuantizeFusionPass)
+            if (op.kind in ('Relu', 'Clip') and self._last_out is not None and self._last_out[1] is x and x._version == self._last_out[2]
+                    and self._last_out[0].kind in ('Conv', 'Gemm')):      # same tensor object AND not modified in place since (residual +=)
+                self._last_out[0].output_cfg.state = QuantizationStates.OVERLAPPED
+            return None
+        hook = self._hooks.get(op.name) if self._hooks else None
+        inputs, qinputs, cfgs = [], [], []
+        if op.input_cfg is not None:
+            inputs.append(x); qinputs.append(self.quantize_function(x, op.input_cfg)); cfgs.append(op.input_cfg)
+            if self._collect and op.input_cfg.state == QuantizationStates.INITIAL: self._emit(x)
+        if op.weight_cfg is not None:
+            w = module.weight
+            wq = self.quantize_function(w.data, op.weight_cfg)          # re-quantised every forward (torch.py:516-518)
+            inputs.append(w.data); qinputs.append(wq); cfgs.append(op.weight_cfg)
+            if wq is not w.data:
+                module.__dict__['_ppq_fp32_weight'] = w.data
+                w.data = wq
+        if hook is not None: hook.pre_forward_hook(inputs=inputs, quant_inputs=qinputs, quant_configs=cfgs)
+        if op.input_cfg is not None and qinputs[0] is not x:
+            return (qinputs[0],) + tuple(args[1:])
+        return None
+
+    def _post(self, module, args, output):
+        op = self._op_of(module)
+        self._calls[id(module)] = self._calls.get(id(module), 0) + 1
+        if self._tracing:
+            self._last_out = (op, output, output._version)
+            return None
+        fp32 = module.__dict__.pop('_ppq_fp32_weight', None)
+        if fp32 is not None: module.weight.data = fp32
+        qout = self.quantize_function(output, op.output_cfg)
+        hook = self._hooks.get(op.name) if self._hooks else None
+        if hook is not None: hook.post_forward_hook(outputs=[output], quant_outputs=[qout], quant_configs=[op.output_cfg])
+        if self._collect and op.output_cfg.state == QuantizationStates.INITIAL: self._emit(output)
+        return qout if qout is not output else None
+
+    def _emit(self, tensor: torch.Tensor):
+        if self._sink is not None: self._sink(len(self._collected), tensor)    # immediate: the k-th observed tensor of this forward
+        self._collected.append(tensor if self._sink is None else None)
+
+    @torch.no_grad()
+    def forward(self, inputs: torch.Tensor, hooks: Optional[dict] = None, collect: bool = False, sink=None):
+        """torch.py:365-410.  `collect=True` returns (output, observed fp32 tensors) for a deferred multi-tensor launch -- only
+        valid when the network does not overwrite them in place; `sink(k, tensor)` observes the k-th tensor immediately."""
+        self._hooks, self._collect, self._sink = hooks, collect or sink is not None, sink
+        self._begin()
+        out = self.model(inputs)
+        collected, self._collected, self._sink = self._collected, None, None
+        return (out, collected) if collect else out
+
+    def observed_configs(self) -> List[TensorQuantizationConfig]:
+        """Configs in the order `collect=True` returns their tensors."""
+        cfgs = []
+        for n in self._order:
+            op = self.operations[n]
+            if op.input_cfg is not None and op.input_cfg.state == QuantizationStates.INITIAL: cfgs.append(op.input_cfg)
+            if op.output_cfg.state == QuantizationStates.INITIAL: cfgs.append(op.output_cfg)
+        return cfgs
+
+    @torch.no_grad()
+    def quantize_parameters(self):
+        """ParameterQuantizePass (optim/parameters.py:172-215): per-channel min/max observers on the weights, rendered to
+        scale/offset by the on-device search."""
+        from .observer import TensorObserverFactroy
+        for n in self._order:
+            op = self.operations[n]
+            if op.weight_cfg is not None and op.weight_cfg.state == QuantizationStates.INITIAL:
+                ob = TensorObserverFactroy.build_observer(n + ':weight', op.weight_cfg)
+                ob.observe(op.module.weight.data)
+                ob.render_quantization_config()
+
+    @torch.no_grad()
+    def bake_parameters(self):
+        """ParameterBakingPass (optim/baking.py:34-47, IR/quantize.py:98-111): quantise each weight once and freeze it."""
+        for n in self._order:
+            op = self.operations[n]
+            if op.weight_cfg is not None and op.weight_cfg.state == QuantizationStates.ACTIVATED:
+                op.module.weight.data = self._quant_fn(op.module.weight.data, op.weight_cfg)
+                op.weight_cfg.state = QuantizationStates.BAKED
+
+
+# ------------------------------------------------------------------------------------------------------------------ calibration drivers
+@torch.no_grad()
+def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=None, to_device=None, deferred: bool = False):
+    """Two-phase calibration of every observed activation through one ArenaCalibrator (statistics arena, one all-reduce per
+    phase, on-device scale search).  `batches` is this rank's share of the calibration set (sample-sharded by the caller).
+    deferred=False observes each tensor as the forward produces it (torchvision networks add residuals in place);
+    deferred=True keeps the tensors alive and issues ONE multi-tensor launch per forward."""
+    from .calibration import ArenaCalibrator
+    cfgs = executor.observed_configs()
+    for c in cfgs: c.observer_algorithm = method
+    dev = next(executor.model.parameters()).device
+    cal = ArenaCalibrator(len(cfgs), dev, method=method, group=group)
+    while True:
+        for x in batches:
+            if to_device is not None: x = to_device(x)
+            if deferred:
+                _, tensors = executor.forward(x, collect=True)
+                cal.observe([t if t.is_contiguous() else t.contiguous() for t in tensors])
+                del tensors
+            else:
+                executor.forward(x, sink=cal.observe_one)
+        if cal.end_phase(): break
+    for i, c in enumerate(cfgs):
+        c.scale, c.offset, c.state = cal.scale[i], cal.offset[i], QuantizationStates.ACTIVATED
+    return cal
+
+
+def e2e_calibration_benchmark(batch: int, steps: int, warmup: int, device, world: int = 1, seed: int = 0):
+    """bench.py's `e2e`: ResNet-50 (random init, BN folded) calibrated end to end through the public API -- images in pinned host
+    memory, H2D copy of every batch inside the timed region (both phases), torch forward with per-forward weight fake-quant,
+    multi-tensor collectors, the two all-reduces, on-device KL search and a D2H read of the resulting scales."""
+    import torch.distributed as dist
+    import torchvision
+    torch.manual_seed(seed)
+    torch.backends.cudnn.benchmark = True
+    model = torchvision.models.resnet50(weights=None).eval()
+    ex = TorchExecutor(model.to(device), torch.zeros(2, 3, 224, 224, device=device))
+    ex.quantize_parameters()
+    g = torch.Generator().manual_seed(seed + 1)
+    host = [torch.rand(batch, 3, 224, 224, generator=g).pin_memory() for _ in range(steps)]
+    stream = torch.cuda.current_stream()
+
+    act_cfgs = ex.observed_configs()
+
+    def reset():
+        for c in act_cfgs: c.state = QuantizationStates.INITIAL
+
+    def run(batches):
+        cal = calibrate_arena(ex, batches, method='kl', to_device=lambda x: x.to(device, non_blocking=True))
+        return cal.scale.cpu()                                            # D2H of the result (synchronises)
+
+    for _ in range(max(warmup, 1)):
+        run(host[:2]); reset()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    scales = run(host)
+    t1.record(stream)
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], device=device); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
+    assert bool(torch.isfinite(scales).all()) and bool((scales > 0).all())
+    return {'value': round(world * steps * batch / (ms * 1e-3), 1), 'unit': 'imgs/s',
+            'h2d_bytes_per_step': 2 * batch * 3 * 224 * 224 * 4, 'd2h_bytes_per_step': int(scales.numel() * 4 / steps) + 1,
+            'ms_per_step': round(ms / steps, 3), 'steps': steps, 'observed_tensors': int(scales.numel()),
+            'what': 'pinned-host images -> H2D -> torch ResNet-50 forward (fp32, cuDNN) with per-forward INT8 per-channel weight fake-quant '
+                    '-> multi-tensor min/max (phase 1) / histogram (phase 2) -> all-reduce -> on-device KL search -> scales D2H'}
