@@ -119,6 +119,14 @@ PPQ_B200_API int ppq_b200_histogram_c(const float *x, int64_t n, int64_t epc, in
 PPQ_B200_API int ppq_b200_histogram_t_dscale(const float *x, int64_t n, const float *hist_scale_dev, int clip_outliers,
                                              int32_t *hist, int64_t bins, void *stream);
 
+/* replaces Quantile_T, sort.cu:6-20, 42-59 (ffi.py:171-176): out[0] = sorted[clip(rn(n*q))], out[1] = sorted[clip(rn(n*(1-q)))],
+ * found by an exact 3-pass radix select on the order-preserving key (no clone, no full sort; same element bit for bit).
+ * `workspace` is DEVICE scratch of ppq_b200_quantile_workspace_bytes() bytes. */
+PPQ_B200_API int64_t ppq_b200_quantile_workspace_bytes(void);
+PPQ_B200_API int ppq_b200_quantile_t(const float *x, int64_t n, float q, float *out2, void *workspace, void *stream);
+/* replaces Isotone_T, sort.cu:23-40, 61-73: out4 = {sorted[n-1], sorted[n-2], sorted[0], sorted[1]} (same workspace). */
+PPQ_B200_API int ppq_b200_isotone_t(const float *x, int64_t n, float *out4, void *workspace, void *stream);
+
 /* ---- multi-tensor collectors (one launch over a table of tensors; the B200-native calibration path) ---------
  * A descriptor lives in DEVICE memory.  `slot` selects the statistics slot in the arena:
  *   minmax arena: float[2 * slots]  ({min, max} per slot);   hist arena: int32[slots * bins];
@@ -155,6 +163,35 @@ PPQ_B200_API int ppq_b200_kl_search(const int32_t *hist_arena, int64_t count, in
 /* replaces compute_mse_loss, ppq/csrc/cpu/hist_mse.cc:3-28 (ffi.py:263-270).  HOST function on HOST memory, exactly
  * like the reference's (it is a serial fp32 accumulation over <= 2048 bins). */
 PPQ_B200_API float ppq_b200_compute_mse_loss(const int64_t *hist, int64_t nbins, int start, int step, int end);
+/* ---- training-pass helpers that share the scalar quantizer ("next" rows) ---------------------------- */
+/* replaces QuantizeTensor_LT_B, linear.cu:235-324: grad_x (STE with clip mask) and grad_s (1 float; zeroed here). */
+PPQ_B200_API int ppq_b200_linear_quant_t_backward(const float *x, const float *dy, int64_t n,
+                                                  const float *scale, const float *offset, int qmin, int qmax, int rounding,
+                                                  float *grad_x, float *grad_s, void *stream);
+/* replaces QuantizeTensor_LC_B, linear.cu:326-433: grad_s has C floats. */
+PPQ_B200_API int ppq_b200_linear_quant_c_backward(const float *x, const float *dy, int64_t n, int64_t epc, int C,
+                                                  const float *scale, const float *offset, int qmin, int qmax, int rounding,
+                                                  float *grad_x, float *grad_s, void *stream);
+/* replace QuantizeTensor_FT_B / _FC_B, floating.cu:133-331. */
+PPQ_B200_API int ppq_b200_float_quant_t_backward(const float *x, const float *dy, int64_t n, const float *scale, const float *offset,
+                                                 int exponent, int mantissa, float clip_min, float clip_max, int rounding,
+                                                 float *grad_x, float *grad_s, void *stream);
+PPQ_B200_API int ppq_b200_float_quant_c_backward(const float *x, const float *dy, int64_t n, int64_t epc, int C,
+                                                 const float *scale, const float *offset,
+                                                 int exponent, int mantissa, float clip_min, float clip_max, int rounding,
+                                                 float *grad_x, float *grad_s, void *stream);
+/* replace TensorClip_T / _C, train.cu:34-113: out = CLIP(value, reference - limit[c], reference + limit[c]). */
+PPQ_B200_API int ppq_b200_tensor_clip_t(const float *value, const float *reference, const float *limit, int64_t n, float *out, void *stream);
+PPQ_B200_API int ppq_b200_tensor_clip_c(const float *value, const float *reference, const float *limit, int64_t n, int64_t epc, int C,
+                                        float *out, void *stream);
+/* replace RoundingLoss_LT / _LC (per_channel = 0 / 1), train.cu:115-176, 224-283, and their _B, :178-222, 285-338. */
+PPQ_B200_API int ppq_b200_rounding_loss(const float *x, int64_t n, int64_t epc, int C, int per_channel,
+                                        const float *scale, const float *offset, int qmin, int qmax, int rounding,
+                                        float *loss, void *stream);
+PPQ_B200_API int ppq_b200_rounding_loss_backward(const float *x, const float *dy, int64_t n, int64_t epc, int C, int per_channel,
+                                                 const float *scale, const float *offset, int qmin, int qmax, int rounding,
+                                                 float *grad_x, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

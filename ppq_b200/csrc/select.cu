@@ -1,0 +1,165 @@
+// select.cu -- exact order statistics without sorting (sm_100a), behind the C ABI of include/ppq_b200.h.
+//
+//   ppq_b200_quantile_t   replaces Quantile_T (/root/reference/ppq/csrc/cuda/sort.cu:6-20, 42-59): the reference clones the
+//                         tensor, thrust::sort's the clone and reads sorted[clip(rn(n*q))] and sorted[clip(rn(n*(1-q)))].
+//   ppq_b200_isotone_t    replaces Isotone_T (sort.cu:23-40, 61-73): sorted[n-1], sorted[n-2], sorted[0], sorted[1].
+//
+// Here: MSD radix *select* on the order-preserving 32-bit key of each float (the same total order thrust's radix sort uses:
+// -NaN < -inf < ... < -0 < +0 < ... < +inf < +NaN), 11 + 11 + 10 bits, both requested ranks resolved together.  Three
+// streaming passes over the input (12 B/element, shared-memory privatised digit histograms) instead of a clone plus a full
+// device sort; no allocation -- the caller provides a small workspace.  The result is the identical element, bit for bit.
+#include "common.cuh"
+#include "../../include/ppq_b200.h"
+
+namespace ppqb {
+
+constexpr int kSelThreads = 1024;
+constexpr int kDigits = 2048;                  // 11-bit digits (the last pass uses 10 bits)
+
+struct SelectState {                           // lives in the caller's workspace
+    unsigned long long hist[2][kDigits];       // per rank: digit histogram of the current pass
+    unsigned int prefix[2];                    // key bits resolved so far (high bits)
+    unsigned int pad_[2];
+    long long rank[2];                         // remaining rank inside the current prefix bucket
+    long long ranks_in[4];
+};
+
+__device__ __forceinline__ uint32_t order_key(float v) {
+    uint32_t b = __float_as_uint(v);
+    if (b == 0x80000000u) b = 0u;          // -0.0 and +0.0 are one key, as in CUB's radix sort (which thrust::sort dispatches to);
+                                           // the selected zero is reported as +0.0 (the reference reports whichever zero its stable
+                                           // sort left at that index -- equal as floats, the sign is not recoverable without a sort)
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+__global__ void select_init_kernel(SelectState *st, long long r0, long long r1) {
+    for (int i = threadIdx.x; i < 2 * kDigits; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
+    if (threadIdx.x == 0) { st->prefix[0] = st->prefix[1] = 0u; st->rank[0] = r0; st->rank[1] = r1; }
+}
+
+// PASS 0: digit = key[31:21];  PASS 1: key[20:10] among keys whose top 11 bits match;  PASS 2: key[9:0] among top-22 matches.
+template <int PASS>
+__global__ void __launch_bounds__(kSelThreads)
+select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restrict__ st) {
+    __shared__ int sh[2][kDigits];
+    for (int i = threadIdx.x; i < 2 * kDigits; i += kSelThreads) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
+    constexpr uint32_t dmask = PASS == 2 ? 0x3FFu : 0x7FFu;
+    constexpr uint32_t pmask = PASS == 0 ? 0u : (PASS == 1 ? 0xFFE00000u : 0xFFFFFC00u);
+    const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
+    const bool same = (p0 == p1);
+    auto visit = [&](float v) {
+        const uint32_t k = order_key(v);
+        const uint32_t hi = k & pmask, d = (k >> shift) & dmask;
+        if (hi == p0) atomicAdd(&sh[0][d], 1);
+        if (!same && hi == p1) atomicAdd(&sh[1][d], 1);
+    };
+    const int64_t first = (int64_t)blockIdx.x * kSelThreads + threadIdx.x, stride = (int64_t)gridDim.x * kSelThreads;
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+        const int64_t n4 = n >> 2;
+        const float4 *x4 = reinterpret_cast<const float4 *>(x);
+        for (int64_t i = first; i < n4; i += 4 * stride) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (i + j * stride < n4) v[j] = ld_stream4(x4 + i + j * stride);
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (i + j * stride < n4) { visit(v[j].x); visit(v[j].y); visit(v[j].z); visit(v[j].w); }
+        }
+        const int64_t t = (n4 << 2) + first;
+        if (t < n) visit(x[t]);
+    } else {
+        for (int64_t i = first; i < n; i += stride) visit(ld_stream1(x + i));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kDigits; i += kSelThreads) {
+        if (sh[0][i]) atomicAdd(&st->hist[0][i], (unsigned long long)sh[0][i]);
+        if (!same && sh[1][i]) atomicAdd(&st->hist[1][i], (unsigned long long)sh[1][i]);
+    }
+}
+
+// One CTA: walk the digit histogram of each rank, pick the digit bucket that contains the rank, extend the prefix.
+template <int PASS>
+__global__ void select_scan_kernel(SelectState *st, float *out, int out_stride) {
+    constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
+    constexpr int digits = PASS == 2 ? 1024 : kDigits;
+    __shared__ unsigned int new_prefix[2];
+    __shared__ long long new_rank[2];
+    const bool same = st->prefix[0] == st->prefix[1];
+    if (threadIdx.x < 2) {
+        const int r = threadIdx.x;
+        const unsigned long long *h = st->hist[(r == 1 && same) ? 0 : r];
+        long long k = st->rank[r];
+        int d = 0;
+        for (; d < digits - 1; d++) { const long long c = (long long)h[d]; if (k < c) break; k -= c; }
+        new_prefix[r] = st->prefix[r] | ((unsigned int)d << shift);
+        new_rank[r] = k;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * kDigits; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
+    if (threadIdx.x < 2) {
+        st->prefix[threadIdx.x] = new_prefix[threadIdx.x];
+        st->rank[threadIdx.x] = new_rank[threadIdx.x];
+        if (PASS == 2) out[threadIdx.x * out_stride] = key_to_float(new_prefix[threadIdx.x]);
+    }
+}
+
+static int select_two(const float *x, int64_t n, long long r0, long long r1, float *out, int out_stride, SelectState *st, cudaStream_t s) {
+    int64_t g = (n + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
+    if (g > kSMs) g = kSMs;
+    if (g < 1) g = 1;
+    select_init_kernel<<<1, 1024, 0, s>>>(st, r0, r1);
+    select_hist_kernel<0><<<(int)g, kSelThreads, 0, s>>>(x, n, st);
+    select_scan_kernel<0><<<1, 1024, 0, s>>>(st, out, out_stride);
+    select_hist_kernel<1><<<(int)g, kSelThreads, 0, s>>>(x, n, st);
+    select_scan_kernel<1><<<1, 1024, 0, s>>>(st, out, out_stride);
+    select_hist_kernel<2><<<(int)g, kSelThreads, 0, s>>>(x, n, st);
+    select_scan_kernel<2><<<1, 1024, 0, s>>>(st, out, out_stride);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ppqb
+
+using namespace ppqb;
+
+extern "C" {
+
+int64_t ppq_b200_quantile_workspace_bytes(void) { return (int64_t)sizeof(SelectState); }
+
+int ppq_b200_quantile_t(const float *x, int64_t n, float q, float *out2, void *workspace, void *stream) {
+    if (n <= 0 || !x || !out2 || !workspace) return (int)cudaErrorInvalidValue;
+    // index arithmetic of _Quantile_T (sort.cu:13-19): int64 * float -> float, __float2int_rn (half-even, saturating), CLIP
+    const float fa = (float)n * q;
+    const float fb = (float)n * (1.0f - q);
+    auto rn = [](float v) -> long long {
+        if (v != v) return 0;
+        if (v >= 2147483648.0f) return 2147483647LL;
+        if (v <= -2147483648.0f) return -2147483648LL;
+        return (long long)__builtin_nearbyintf(v);
+    };
+    long long a = rn(fa), b = rn(fb);
+    // the reference clips with CLIP<int>(pos, 0, n - 1) where n - 1 is converted to int
+    const long long last = (long long)(int)(n - 1);
+    a = a > last ? last : (a < 0 ? 0 : a);
+    b = b > last ? last : (b < 0 ? 0 : b);
+    return select_two(x, n, a, b, out2, 1, (SelectState *)workspace, (cudaStream_t)stream);
+}
+
+int ppq_b200_isotone_t(const float *x, int64_t n, float *out4, void *workspace, void *stream) {
+    if (n <= 0 || !x || !out4 || !workspace) return (int)cudaErrorInvalidValue;
+    SelectState *st = (SelectState *)workspace;
+    if (n == 1) {
+        int rc = select_two(x, n, 0, 0, out4, 1, st, (cudaStream_t)stream);
+        if (rc) return rc;
+        return select_two(x, n, 0, 0, out4 + 2, 1, st, (cudaStream_t)stream);
+    }
+    // out = { sorted[n-1], sorted[n-2], sorted[0], sorted[1] }
+    int rc = select_two(x, n, n - 1, n - 2, out4, 1, st, (cudaStream_t)stream);
+    if (rc) return rc;
+    return select_two(x, n, 0, 1, out4 + 2, 1, st, (cudaStream_t)stream);
+}
+
+}  // extern "C"

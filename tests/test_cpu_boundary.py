@@ -51,9 +51,13 @@ def test_library_contains_sm100a_code_only(built):
 def test_extension_loads_and_exports_reference_names(built):
     from ppq_b200.ffi import CUDA, extension
     ext = extension()
-    # the hot-path names of the reference table (ppq/csrc/export.cc:9-33); the rest of the 20 are checked in test_reference_table_complete
-    for name in ['Histogram_T', 'Histogram_Asymmetric_T', 'Histogram_C', 'QuantizeTensor_LT', 'QuantizeTensor_LC',
-                 'QuantizeTensor_FT', 'QuantizeTensor_FC', 'compute_mse_loss']:
+    # the complete reference table (ppq/csrc/export.cc:9-33): 20 names
+    table = ['Quantile_T', 'Histogram_T', 'Histogram_Asymmetric_T', 'Histogram_C', 'QuantizeTensor_LT', 'QuantizeTensor_LC',
+             'QuantizeTensor_LT_B', 'QuantizeTensor_LC_B', 'QuantizeTensor_FT', 'QuantizeTensor_FC', 'QuantizeTensor_FT_B',
+             'QuantizeTensor_FC_B', 'TensorClip_T', 'TensorClip_C', 'RoundingLoss_LT', 'RoundingLoss_LC', 'RoundingLoss_LT_B',
+             'RoundingLoss_LC_B', 'Isotone_T', 'compute_mse_loss']
+    assert len(table) == 20
+    for name in table:
         assert hasattr(ext, name), name
     for name in ['LinearQuantize_T', 'LinearQuantize_C', 'Histogram_T', 'Histogram_Asymmetric_T', 'Histogram_C', 'Quantile',
                  'compute_mse_loss', 'FloatingQuantize_T', 'FloatingQuantize_C', 'LinearQuantize_T_B', 'LinearQuantize_C_B',

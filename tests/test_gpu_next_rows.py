@@ -1,0 +1,199 @@
+"""GPU parity of the "next" rows: Quantile_T / Isotone_T by radix select, LSQ backward, float backward,
+TensorClip, RoundingLoss -- against the reference's own CUDA kernels (oracle/_ref) where present, and against the oracle /
+the torch formulas of the reference's test (tests/test_cuda_kernel.py:66-143) otherwise.
+Element-wise outputs must be bit-identical; scalar fp32 reductions (grad_s, loss) to 1e-4 relative (the reference's own bar is SNR 1e-3)."""
+import importlib.util
+import os
+from math import sqrt
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+REF_SO = os.path.join(ROOT, 'oracle', '_ref', 'PPQ_Cuda_Impls_ref.so')
+
+
+@pytest.fixture(scope='module')
+def ext():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from ppq_b200.ffi import extension
+    return extension()
+
+
+@pytest.fixture(scope='module')
+def ref():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    if not os.path.exists(REF_SO):
+        return None
+    spec = importlib.util.spec_from_file_location('PPQ_Cuda_Impls_ref', REF_SO)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def same_bits(a, b):
+    return torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32))
+
+
+def close(a, b, rtol=1e-4, atol=1e-6):
+    return torch.allclose(a.double(), b.double(), rtol=rtol, atol=atol)
+
+
+def test_quantile_vs_sort_oracle_and_reference(ext, ref, oracle):
+    g = torch.Generator(device='cuda').manual_seed(0)
+    for n in (1, 2, 3, 17, 1000, 4099, 401408, (1 << 21) + 5):
+        for kind in ('randn', 'relu', 'const', 'ints'):
+            x = torch.randn(n, device='cuda', generator=g) * 3
+            if kind == 'relu': x = torch.relu(x)
+            if kind == 'const': x = torch.full((n,), -1.25, device='cuda')
+            if kind == 'ints': x = torch.randint(-5, 5, (n,), device='cuda', generator=g).float()
+            if n > 8: x[3] = -0.0; x[5] = 0.0
+            for q in (0.9999, 0.999, 0.5, 1.0, 0.0):
+                got = ext.Quantile_T(x, q)
+                srt = torch.sort(x)[0]
+                fa = np.float32(n) * np.float32(q); fb = np.float32(n) * (np.float32(1) - np.float32(q))
+                ia = int(min(max(np.rint(fa), 0), n - 1)); ib = int(min(max(np.rint(fb), 0), n - 1))
+                want = torch.stack([srt[ia], srt[ib]])
+                assert torch.equal(got, want), (n, kind, q, got, want)          # value equality (-0.0 == +0.0)
+                if n <= 4099:
+                    assert np.array_equal(got.cpu().numpy(), oracle.quantile_t(x.cpu().numpy(), q)), (n, kind, q)
+                if ref is not None and n > 1:
+                    r = ref.Quantile_T(x, q)
+                    assert torch.equal(got, r) and same_bits(torch.where(got == 0, torch.zeros_like(got), got), torch.where(r == 0, torch.zeros_like(r), r)), (n, kind, q)
+    # unaligned view + non-contiguous input
+    base = torch.randn(10007, device='cuda', generator=g)
+    v = base[1:]
+    assert torch.equal(ext.Quantile_T(v, 0.99), torch.stack([torch.sort(v)[0][int(np.rint(np.float32(v.numel()) * np.float32(0.99)))],
+                                                             torch.sort(v)[0][int(np.rint(np.float32(v.numel()) * (np.float32(1) - np.float32(0.99))))]]))
+
+
+def test_isotone_top2_bottom2(ext, ref):
+    g = torch.Generator(device='cuda').manual_seed(1)
+    for n in (1, 2, 5, 1000, 100003):
+        x = torch.randn(n, device='cuda', generator=g)
+        got = ext.Isotone_T(x)
+        s = torch.sort(x)[0]
+        want = torch.stack([s[-1], s[-2], s[0], s[1]]) if n > 1 else torch.stack([s[0]] * 4)
+        assert torch.equal(got, want), n
+        if ref is not None and n > 1:
+            assert same_bits(got, ref.Isotone_T(x)), n
+
+
+def test_percentile_observer_end_to_end(ext):
+    from ppq_b200 import LinearQuantizationConfig, QuantizationStates
+    from ppq_b200.observer import Observer
+    g = torch.Generator(device='cuda').manual_seed(2)
+    data = [torch.randn(4, 16, 28, 28, device='cuda', generator=g) for _ in range(4)]
+    cfg = LinearQuantizationConfig(symmetrical=True, calibration='percentile')
+    ob = Observer(cfg)
+    for x in data: ob.observe(x)
+    ob.render_quantization_config()
+    assert cfg.state == QuantizationStates.ACTIVATED
+    pairs = []
+    for x in data:
+        s = torch.sort(x.flatten())[0]; n = s.numel()
+        pairs.append(torch.stack([s[int(np.rint(np.float32(n) * np.float32(0.9999)))], s[int(np.rint(np.float32(n) * (np.float32(1) - np.float32(0.9999))))]]))
+    m = torch.stack(pairs).float().mean(dim=0).cpu()
+    want = 2 * max(abs(m[0].item()), abs(m[1].item())) / 255
+    assert cfg.scale.item() == np.float32(want) and cfg.offset.item() == 0
+
+
+def lsq_reference(value, dy, scale, offset, qmin, qmax, c=None):
+    """tests/test_cuda_kernel.py:67-79 / 99-114 (the reference's own torch formula)."""
+    if c is not None:
+        shape = [1 if a != c else -1 for a in range(value.ndim)]
+        scale, offset = scale.view(shape), offset.view(shape)
+    qt = torch.round(value / scale) + offset
+    cl = qt.clip(qmin, qmax)
+    dx = torch.where(cl != qt, torch.zeros_like(dy), dy)
+    ds = torch.where(cl == qt, (((qt - offset) * scale) - value) * dy / scale, torch.zeros_like(dy))
+    ds = ds + torch.where(qt > qmax, (qmax - offset) * dy, torch.zeros_like(dy))
+    ds = ds + torch.where(qt < qmin, (qmin - offset) * dy, torch.zeros_like(dy))
+    return dx, ds
+
+
+def test_lsq_backward_t_and_c(ext, ref):
+    g = torch.Generator(device='cuda').manual_seed(3)
+    for shape, c in (([1, 1, 1, 1], 1), ([5, 12, 13, 4], 1), ([12, 74, 15, 41], 1), ([501, 7, 73, 1], 0), ([10, 10, 14, 47], 3), ([8192 * 3], 0)):
+        for sym in (True, False):
+            t = torch.rand(shape, device='cuda', generator=g) * 50
+            dy = torch.rand(shape, device='cuda', generator=g)
+            s = torch.rand(1, device='cuda', generator=g) + 0.01
+            o = torch.zeros(1, device='cuda') if sym else torch.randint(0, 255, (1,), device='cuda', generator=g).float()
+            gx, gs = ext.QuantizeTensor_LT_B(t, s, o, dy, 0, 255, 0)
+            dx, ds = lsq_reference(t, dy, s, o, 0, 255)
+            assert torch.equal(gx, dx), (shape, sym)
+            assert close(gs, (ds.double().sum() / sqrt(t.numel() * 255)).float().view(1), rtol=1e-3), (shape, sym)
+            if ref is not None:
+                rx, rs = ref.QuantizeTensor_LT_B(t, s, o, dy, 0, 255, 0)
+                assert same_bits(gx, rx), (shape, sym)
+                # the reference kernel block-reduces inside `if (index < N)` with __syncthreads (linear.cu:252-281): its grad_s is only
+                # well defined when N is a multiple of the 1024-thread block
+                if t.numel() % 1024 == 0: assert close(gs, rs, rtol=1e-3), (shape, sym)
+            if len(shape) > 1:
+                C = shape[c]
+                sc = torch.rand(C, device='cuda', generator=g) + 0.01
+                oc = torch.zeros(C, device='cuda') if sym else torch.randint(0, 255, (C,), device='cuda', generator=g).float()
+                gx, gs = ext.QuantizeTensor_LC_B(t, sc, oc, dy, 0, 255, 0, c)
+                dx, ds = lsq_reference(t, dy, sc, oc, 0, 255, c)
+                assert torch.equal(gx, dx), (shape, sym, 'C')
+                want = ds.double().transpose(0, c).flatten(1).sum(dim=-1) / sqrt(t.numel() * 255)      # the kernel's factor is rsqrt(N * qmax) (linear.cu:402)
+                assert close(gs, want.float(), rtol=1e-3, atol=1e-5), (shape, sym, 'C')
+                if ref is not None:
+                    rx, rs = ref.QuantizeTensor_LC_B(t, sc, oc, dy, 0, 255, 0, c)
+                    assert same_bits(gx, rx) and close(gs, rs, rtol=1e-3, atol=1e-5), (shape, sym, 'C')
+
+
+def test_float_backward(ext, ref):
+    g = torch.Generator(device='cuda').manual_seed(4)
+    x = torch.randn(1024 * 64, device='cuda', generator=g) * 200          # sizes on which the reference kernel's block-wide syncs are safe
+    dy = torch.rand(x.shape, device='cuda', generator=g)
+    s, o = torch.tensor([0.5], device='cuda'), torch.tensor([0.0], device='cuda')
+    gx, gs = ext.QuantizeTensor_FT_B(x, s, o, dy, 4, 3, -448.0, 448.0, 0)
+    u = x / s
+    sat = (u > 449) | (u < -449)          # the backward kernel quantises with the clip range widened by one (floating.cu:157-158)
+    assert torch.equal(gx, torch.where(sat, torch.zeros_like(dy), dy))
+    if ref is not None:
+        rx, rs = ref.QuantizeTensor_FT_B(x, s, o, dy, 4, 3, -448.0, 448.0, 0)
+        assert same_bits(gx, rx) and close(gs, rs, rtol=2e-3)
+    xc = x.view(8, 8, 1024)
+    sc = 2.0 ** torch.randint(-3, 3, (8,), device='cuda', generator=g).float(); oc = torch.zeros(8, device='cuda')
+    gx, gs = ext.QuantizeTensor_FC_B(xc, sc, oc, dy.view(8, 8, 1024), 4, 3, -448.0, 448.0, 0, 1)
+    if ref is not None:
+        rx, rs = ref.QuantizeTensor_FC_B(xc, sc, oc, dy.view(8, 8, 1024), 4, 3, -448.0, 448.0, 0, 1)
+        assert same_bits(gx, rx) and close(gs, rs, rtol=2e-3, atol=1e-5)
+
+
+def test_tensor_clip_and_rounding_loss(ext, ref):
+    g = torch.Generator(device='cuda').manual_seed(5)
+    for shape, c in (([7], 0), ([5, 12, 13, 4], 1), ([64, 32, 3, 3], 0), ([3, 1000], 1)):
+        v = torch.randn(shape, device='cuda', generator=g)
+        r = torch.randn(shape, device='cuda', generator=g)
+        lim = torch.rand(1, device='cuda', generator=g)
+        want = torch.minimum(torch.maximum(v, r - lim), r + lim)
+        assert torch.equal(ext.TensorClip_T(v, r, lim), want), shape
+        C = shape[c]
+        limc = torch.rand(C, device='cuda', generator=g)
+        view = [1 if a != c else -1 for a in range(len(shape))]
+        wantc = torch.minimum(torch.maximum(v, r - limc.view(view)), r + limc.view(view))
+        assert torch.equal(ext.TensorClip_C(v, r, limc, c), wantc), shape
+        s = torch.rand(1, device='cuda', generator=g) * 0.1 + 0.01; o = torch.tensor([3.0], device='cuda')
+        sc = torch.rand(C, device='cuda', generator=g) * 0.1 + 0.01; oc = torch.randint(-3, 3, (C,), device='cuda', generator=g).float()
+        dyy = torch.tensor([0.7], device='cuda')
+        loss_t, loss_c = ext.RoundingLoss_LT(v, s, o, -128, 127, 0), ext.RoundingLoss_LC(v, sc, oc, -128, 127, c, 0)
+        gt, gc = ext.RoundingLoss_LT_B(v, dyy, s, o, -128, 127, 0), ext.RoundingLoss_LC_B(v, dyy, sc, oc, -128, 127, c, 0)
+        # torch restatement of train.cu:125-141
+        q = torch.clamp(torch.round(v / s) + o, -128, 127); deq = (q - o) * s
+        clipped = (v > s * (127 - o)) | (v < s * (-128 - o))
+        assert close(loss_t, (torch.where(clipped, torch.zeros_like(v), (deq - v).abs()).double().sum() / sqrt(v.numel())).float().view(1), rtol=1e-4)
+        assert torch.equal(gt, torch.where(clipped, torch.zeros_like(v), torch.where(v > deq, 1.0, -1.0) * dyy) / torch.sqrt(torch.tensor(float(v.numel()), device='cuda')))
+        if ref is not None:
+            assert same_bits(ext.TensorClip_T(v, r, lim), ref.TensorClip_T(v, r, lim)) and same_bits(ext.TensorClip_C(v, r, limc, c), ref.TensorClip_C(v, r, limc, c))
+            assert close(loss_t, ref.RoundingLoss_LT(v, s, o, -128, 127, 0)) and close(loss_c, ref.RoundingLoss_LC(v, sc, oc, -128, 127, c, 0))
+            assert same_bits(gt, ref.RoundingLoss_LT_B(v, dyy, s, o, -128, 127, 0)), shape
+            assert same_bits(gc, ref.RoundingLoss_LC_B(v, dyy, sc, oc, -128, 127, c, 0)), shape
