@@ -217,9 +217,12 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     cal.launches = 0; launches[0] = 0
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push('timed')
     t0.record(stream)
     scales = calibrate(args.steps, True)
     t1.record(stream)
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
     barrier()
     sampler.stop_flag = True
     ms = t0.elapsed_time(t1)
@@ -253,7 +256,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         result['fakequant'] = fakequant_sweep(ext, device, peak)
         result['e2e'] = run_e2e(args, device, world) if not args.no_e2e else None
-        result['cpu_baseline'] = cpu_baseline(args, sample_steps=1)
+        result['cpu_baseline'] = cpu_baseline(args, sample_steps=1) if not args.no_cpu_baseline else None
     elif not args.no_e2e:
         run_e2e(args, device, world)
     return result
@@ -303,7 +306,7 @@ def cpu_steps(batch, steps, seed=0):
     """The reference's USING_CUDA_KERNEL=False path on the host cores, restated in oracle/ with torch CPU ops
     (qfunction/linear.py:73-81, observer/range.py:91-92, :183, :190-282).  Returns seconds for `steps` calibration batches (both phases)."""
     import oracle as ora
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(ora.host_threads())
     acts, weights = resnet50_tensor_table()
     g = torch.Generator().manual_seed(seed)
     ts = []
@@ -331,27 +334,41 @@ def cpu_steps(batch, steps, seed=0):
 
 
 def cpu_baseline(args, sample_steps):
-    secs = cpu_steps(args.batch, sample_steps)
-    return {'value': round(sample_steps * args.batch / secs, 2), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f'{sample_steps} calibration batches of {args.batch} images (both phases + KL search), torch CPU ops, '
-                      f'oracle/ restatement of the reference USING_CUDA_KERNEL=False path; {secs:.1f} s'}
+    """Bounded sample: one calibration batch of 1 image first; if that took < 5 s the sample grows to 4 images (still one batch)."""
+    import oracle as ora
+    b = 1
+    secs = cpu_steps(b, sample_steps)
+    if secs < 5.0:
+        b = 4
+        secs = cpu_steps(b, sample_steps)
+    return {'value': round(sample_steps * b / secs, 2), 'unit': UNIT, 'cores': ora.host_threads(), 'kind': 'port',
+            'sample': f'{sample_steps} calibration batch of {b} image(s) (the GPU arm uses {args.batch}): per-forward weight fake-quant, min/max + histc over the '
+                      f'106 activation tensors, KL search; torch CPU ops (oracle/ restatement of the reference USING_CUDA_KERNEL=False path) on '
+                      f'{ora.host_threads()} threads (host reports {os.cpu_count()} CPUs); {secs:.1f} s'}
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the reference's own CPU implementation of the path (USING_CUDA_KERNEL=False), end to end -- images in host
+    memory, torch CPU forward of ResNet-50 with per-forward weight fake-quant, min/max + histc observers, CPU KL search
+    (oracle/cpu_pipeline.py, a port: the reference package itself cannot travel to the GPU box and needs `onnx`).  Each step is a
+    bounded sample: the calibration batch is `--ref-batch` images (default 8) so that K steps end within minutes."""
     if rank != 0: return None
-    steps = min(args.steps, 4)
-    for _ in range(min(args.warmup, 1)): cpu_steps(args.batch, 1)
-    secs = cpu_steps(args.batch, steps)
-    v = round(steps * args.batch / secs, 2)
-    acts, weights = resnet50_tensor_table()
+    import oracle as ora
+    from oracle.cpu_pipeline import resnet50_cpu_calibration
+    torch.set_num_threads(ora.host_threads())
+    steps = max(2, min(args.steps, 4))
+    _, probe, _ = resnet50_cpu_calibration(batch=1, steps=1)                 # also the warm-up; sizes the bounded sample
+    if probe * args.ref_batch * steps > 90: args.ref_batch = max(1, int(90 / (probe * steps)))
+    v, secs, T = resnet50_cpu_calibration(batch=args.ref_batch, steps=steps)
+    v = round(v, 2)
     return {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': round(secs / steps * 1e3, 2), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': {'workload': 'ResNet-50 RuntimeCalibrationPass (minmax + KL 4096-bin histogram), 3x224x224 samples', 'batch': args.batch,
-                       'observed_tensors': len(acts), 'weight_tensors': len(weights), 'parallelism': 'host cores, 1 process'},
+            'config': {'workload': 'ResNet-50 RuntimeCalibrationPass (minmax + KL 4096-bin histogram), 3x224x224 samples', 'batch': args.ref_batch,
+                       'observed_tensors': T, 'parallelism': f'host cores ({torch.get_num_threads()} threads of {os.cpu_count()} reported CPUs), 1 process', 'timed_steps': steps},
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                             'sample': f'each step = one calibration batch of {args.batch} images; {steps} of the {args.steps} requested steps timed '
-                                       f'(bounded sample), torch CPU ops on {torch.get_num_threads()} threads'},
+                             'sample': f'{steps} calibration batches of {args.ref_batch} images, both phases + KL search, end to end incl. the torch CPU forward '
+                                       f'({secs:.1f} s on {torch.get_num_threads()} threads)'},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
 
 
@@ -364,6 +381,8 @@ def main():
     ap.add_argument('--rotate', type=int, default=4, help='distinct activation sets cycled through (each > L2)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='profiling runs only')
+    ap.add_argument('--ref-batch', type=int, default=8, help='calibration batch of the CPU reference arm (bounded sample)')
     ap.add_argument('--per-tensor-weight-launches', action='store_true', help='one QuantizeTensor_LC launch per weight (the reference flow) instead of the multi-tensor launch')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local_rank = int(os.environ.get('LOCAL_RANK', 0))

@@ -38,6 +38,25 @@ RND_HALF_EVEN, RND_HALF_UP, RND_HALF_DOWN, RND_HALF_TOWARDS_ZERO = 0, 1, 2, 3
 RND_HALF_FAR_FROM_ZERO, RND_TO_NEAR_INT, RND_UP, RND_DOWN = 4, 5, 6, 7
 
 
+def host_threads() -> int:
+    """CPU threads this process may really use: the scheduler affinity mask capped by the cgroup CPU quota.  os.cpu_count() reports
+    the whole host (128 on the B200 boxes) even when the container is limited to a few cores; running torch CPU ops with one thread
+    per *host* core then oversubscribes the quota by an order of magnitude."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    for path in ('/sys/fs/cgroup/cpu.max', '/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+        try:
+            txt = open(path).read().split()
+            if path.endswith('cpu.max'):
+                if txt[0] != 'max': n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0]); per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+                if q > 0: n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, 'ppq_oracle.c')
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):

@@ -14,6 +14,7 @@
 #include "ops.cuh"
 #include "../../include/ppq_b200.h"
 #include "variants.h"
+#include <string.h>
 
 namespace ppqb {
 
@@ -227,6 +228,19 @@ static int launch_channel(const float *x, OutT *y, int64_t n, int64_t epc, int C
     return (int)cudaGetLastError();
 }
 
+// Host twin of the fast-path condition (see FloatOp<MODE, FAST> in ops.cuh).
+static inline bool float_fast_path_ok(int E, int M, float cmin, float cmax) {
+    auto f2u = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    auto u2f = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+    const int emin = -(1 << (E - 1)) + 1, emax = 1 << (E - 1);
+    const uint32_t top = ~(0x007FFFFFu >> M) & 0x007FFFFFu;
+    const float tmax = u2f((uint32_t)((emax + 127) << 23) + top);
+    const float hi = cmax < tmax ? cmax : tmax, lo = cmin > -tmax ? cmin : -tmax;
+    const uint32_t thresh = (uint32_t)(emin + 1 + 127) << 23, half_minus1 = (1u << (22 - M)) - 1u, keep = ~((1u << (23 - M)) - 1u);
+    const uint32_t hb = f2u(hi) & 0x7FFFFFFFu, lb = f2u(lo) & 0x7FFFFFFFu;
+    return hi > 0.f && lo < 0.f && hb >= thresh && lb >= thresh && ((hb + half_minus1) & keep) == hb && ((lb + half_minus1) & keep) == lb;
+}
+
 static inline bool valid_fp_format(int E, int M) {
     // The reference forms min_subnormal with an int shift `1 << (2^(E-1) + M - 2)` (common.cuh:209): defined only
     // while that shift is in 0..30, which also keeps every constant a normal fp32.  E4M3, E5M2, E5M10 (fp16) are inside.
@@ -301,8 +315,11 @@ int ppq_b200_float_quant_t(const float *x, float *y, int64_t n, const float *sca
                            int exponent, int mantissa, float clip_min, float clip_max, int rounding, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!valid_fp_format(exponent, mantissa)) return (int)cudaErrorInvalidValue;
-    if (rounding == RND_HALF_EVEN)
+    if (rounding == RND_HALF_EVEN) {
+        if (float_fast_path_ok(exponent, mantissa, clip_min, clip_max))
+            return launch_tensor<FloatOp<0, true>, float>(x, y, n, scale, offset, {exponent, mantissa, 0, clip_min, clip_max}, st);
         return launch_tensor<FloatOp<0>, float>(x, y, n, scale, offset, {exponent, mantissa, 0, clip_min, clip_max}, st);
+    }
     return launch_tensor<FloatOp<-1>, float>(x, y, n, scale, offset, {exponent, mantissa, rounding, clip_min, clip_max}, st);
 }
 
@@ -310,8 +327,11 @@ int ppq_b200_float_quant_c(const float *x, float *y, int64_t n, int64_t epc, int
                            int exponent, int mantissa, float clip_min, float clip_max, int rounding, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!valid_fp_format(exponent, mantissa)) return (int)cudaErrorInvalidValue;
-    if (rounding == RND_HALF_EVEN)
+    if (rounding == RND_HALF_EVEN) {
+        if (float_fast_path_ok(exponent, mantissa, clip_min, clip_max))
+            return launch_channel<FloatOp<0, true>, float>(x, y, n, epc, C, scale, offset, {exponent, mantissa, 0, clip_min, clip_max}, st);
         return launch_channel<FloatOp<0>, float>(x, y, n, epc, C, scale, offset, {exponent, mantissa, 0, clip_min, clip_max}, st);
+    }
     return launch_channel<FloatOp<-1>, float>(x, y, n, epc, C, scale, offset, {exponent, mantissa, rounding, clip_min, clip_max}, st);
 }
 

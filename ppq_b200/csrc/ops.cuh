@@ -46,12 +46,15 @@ struct LinearOp {
     }
 };
 
-template <int MODE>
+// FAST (HALF_EVEN only, chosen on the host by float_fast_path_ok): the branch-free path, valid when both saturation bounds are
+// fixed points of the rounding (lie on the FP(E,M) grid), so that round(clamp(u)) equals the reference's early returns and its
+// final CLIP is a no-op.
+template <int MODE, bool FAST = false>
 struct FloatOp {
     struct Params { int E, M, mode; float cmin, cmax; };
     struct Plan {
         float hi, lo, cmin, cmax, min_sub, inv_min_sub, sub_magic;
-        uint32_t sub_thresh_bits, half_minus1, keep_mask; int M, mode; bool fast;
+        uint32_t sub_thresh_bits, half_minus1, keep_mask; int M, mode;
         __device__ __forceinline__ explicit Plan(const Params &p) : cmin(p.cmin), cmax(p.cmax), M(p.M), mode(p.mode) {
             const int emin = -(1 << (p.E - 1)) + 1, emax = 1 << (p.E - 1);
             const uint32_t top = ~(0x007FFFFFu >> p.M) & 0x007FFFFFu;
@@ -65,11 +68,6 @@ struct FloatOp {
             sub_thresh_bits = (uint32_t)(emin + 1 + 127) << 23;                         // |u| < 2^(emin+1) -> subnormal grid
             half_minus1 = (1u << (22 - p.M)) - 1u;
             keep_mask = ~((1u << (23 - p.M)) - 1u);
-            // Branch-free fast path (HALF_EVEN only): valid when both saturation bounds are fixed points of the rounding, i.e.
-            // lie on the FP(E,M) grid, so that round(clamp(u)) == the reference's early returns and its final CLIP is a no-op.
-            const uint32_t hb = __float_as_uint(hi) & 0x7FFFFFFFu, lb = __float_as_uint(lo) & 0x7FFFFFFFu;
-            fast = (hi > 0.f) && (lo < 0.f) && hb >= sub_thresh_bits && lb >= sub_thresh_bits &&
-                   (((hb + half_minus1) & keep_mask) == hb) && (((lb + half_minus1) & keep_mask) == lb) && hi <= p.cmax && lo >= p.cmin;
         }
     };
     const Plan &pl; ExactDiv d; float off;
@@ -77,8 +75,8 @@ struct FloatOp {
     static constexpr float kDivLimit = 1.15e18f;                                        // ~2^60: beyond this use div.rn
     // u = x / s already computed exactly; returns the value on the FP(E,M) grid
     __device__ __forceinline__ float grid(float u) const {
-        if constexpr (MODE == RND_HALF_EVEN) {
-            if (pl.fast) {
+        if constexpr (FAST) {
+            {
                 const float uc = fmin_nan(fmax_nan(u, pl.lo), pl.hi);                   // NaN stays NaN (canonical), like the comparisons upstream
                 const uint32_t b = __float_as_uint(uc), mag = b & 0x7FFFFFFFu;
                 // normal range: round the magnitude's discarded mantissa bits half-DOWN (an exact tie keeps the lower value,

@@ -170,6 +170,15 @@ class TorchExecutor:
             if op.output_cfg.state == QuantizationStates.INITIAL: cfgs.append(op.output_cfg)
         return cfgs
 
+    def observed_configs_all(self) -> List[TensorQuantizationConfig]:
+        """All activation configs that take part in calibration, whatever their current state (same order as observed_configs())."""
+        cfgs = []
+        for n in self._order:
+            op = self.operations[n]
+            if op.input_cfg is not None: cfgs.append(op.input_cfg)
+            if op.output_cfg.state != QuantizationStates.OVERLAPPED: cfgs.append(op.output_cfg)
+        return cfgs
+
     @torch.no_grad()
     def quantize_parameters(self):
         """ParameterQuantizePass (optim/parameters.py:172-215): per-channel min/max observers on the weights, rendered to
@@ -194,18 +203,43 @@ class TorchExecutor:
 
 # ------------------------------------------------------------------------------------------------------------------ calibration drivers
 @torch.no_grad()
-def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=None, to_device=None, deferred: bool = False):
+def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=None, to_device=None, deferred: bool = False,
+                    graphs: bool = False):
     """Two-phase calibration of every observed activation through one ArenaCalibrator (statistics arena, one all-reduce per
     phase, on-device scale search).  `batches` is this rank's share of the calibration set (sample-sharded by the caller).
     deferred=False observes each tensor as the forward produces it (torchvision networks add residuals in place);
-    deferred=True keeps the tensors alive and issues ONE multi-tensor launch per forward."""
+    deferred=True keeps the tensors alive and issues ONE multi-tensor launch per forward;
+    graphs=True captures one forward per phase -- network kernels, per-forward weight fake-quant and the collectors -- into a CUDA
+    graph and replays it for every batch (fixed batch shape): the ~230 launches of a ResNet-50 forward cost one graph launch."""
     from .calibration import ArenaCalibrator
     cfgs = executor.observed_configs()
     for c in cfgs: c.observer_algorithm = method
     dev = next(executor.model.parameters()).device
     cal = ArenaCalibrator(len(cfgs), dev, method=method, group=group)
+    static_in = None
     while True:
+        graph = None
         for x in batches:
+            if graphs:
+                if static_in is None:
+                    static_in = torch.empty(x.shape, dtype=torch.float32, device=dev)
+                static_in.copy_(x, non_blocking=True)
+                if graph is None:
+                    # eager run on a side stream first (cuDNN autotuning, lazy initialisation), statistics restored afterwards:
+                    # min/max are idempotent under re-observation, histogram counts are not
+                    keep_mm, keep_h = cal.minmax.clone(), cal.hist.clone()
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        executor.forward(static_in, sink=cal.observe_one)
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    cal.minmax.copy_(keep_mm); cal.hist.copy_(keep_h)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        executor.forward(static_in, sink=cal.observe_one)
+                    cal.minmax.copy_(keep_mm); cal.hist.copy_(keep_h)      # capture does not execute, but stay safe
+                graph.replay()
+                continue
             if to_device is not None: x = to_device(x)
             if deferred:
                 _, tensors = executor.forward(x, collect=True)
@@ -219,7 +253,7 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
     return cal
 
 
-def e2e_calibration_benchmark(batch: int, steps: int, warmup: int, device, world: int = 1, seed: int = 0):
+def e2e_calibration_benchmark(batch: int, steps: int, warmup: int, device, world: int = 1, seed: int = 0, graphs: bool = True):
     """bench.py's `e2e`: ResNet-50 (random init, BN folded) calibrated end to end through the public API -- images in pinned host
     memory, H2D copy of every batch inside the timed region (both phases), torch forward with per-forward weight fake-quant,
     multi-tensor collectors, the two all-reduces, on-device KL search and a D2H read of the resulting scales."""
@@ -240,7 +274,7 @@ def e2e_calibration_benchmark(batch: int, steps: int, warmup: int, device, world
         for c in act_cfgs: c.state = QuantizationStates.INITIAL
 
     def run(batches):
-        cal = calibrate_arena(ex, batches, method='kl', to_device=lambda x: x.to(device, non_blocking=True))
+        cal = calibrate_arena(ex, batches, method='kl', to_device=lambda x: x.to(device, non_blocking=True), graphs=graphs)
         return cal.scale.cpu()                                            # D2H of the result (synchronises)
 
     for _ in range(max(warmup, 1)):
@@ -259,6 +293,6 @@ def e2e_calibration_benchmark(batch: int, steps: int, warmup: int, device, world
     assert bool(torch.isfinite(scales).all()) and bool((scales > 0).all())
     return {'value': round(world * steps * batch / (ms * 1e-3), 1), 'unit': 'imgs/s',
             'h2d_bytes_per_step': 2 * batch * 3 * 224 * 224 * 4, 'd2h_bytes_per_step': int(scales.numel() * 4 / steps) + 1,
-            'ms_per_step': round(ms / steps, 3), 'steps': steps, 'observed_tensors': int(scales.numel()),
+            'ms_per_step': round(ms / steps, 3), 'steps': steps, 'observed_tensors': int(scales.numel()), 'cuda_graphs': graphs,
             'what': 'pinned-host images -> H2D -> torch ResNet-50 forward (fp32, cuDNN) with per-forward INT8 per-channel weight fake-quant '
                     '-> multi-tensor min/max (phase 1) / histogram (phase 2) -> all-reduce -> on-device KL search -> scales D2H'}

@@ -1,0 +1,173 @@
+"""BASELINE.json configs 3-5 as parity cases (config 1 is in test_gpu_parity.py, config 2 is bench.py's workload), plus the host-side
+pieces of the path that sit above the kernels: FP8 observers, dynamic quantisation, the module executor and the calibration drivers."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ext():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from ppq_b200.ffi import extension
+    return extension()
+
+
+def bits(t):
+    return t.detach().cpu().numpy().view(np.uint32)
+
+
+def test_config3_mobilenetv2_per_channel_weights(ext, oracle):
+    """Config 3: per-channel INT8 ChannelwiseLinearQuant over the Conv/Linear weights of MobileNetV2 (53 tensors, 3.47 M elements, 17 depth-wise
+    layers with epc = 9): scales from the on-device per-channel min-max search, fake-quant by single launches AND by the one-launch multi-tensor
+    kernel, both bit-exact vs the oracle."""
+    import torchvision
+    from ppq_b200 import LinearQuantizationConfig
+    from ppq_b200.calibration import MultiWeightQuantizer
+    from ppq_b200.observer import Observer
+    from ppq_b200.qfunction import PPQLinearQuant_toInt, PPQuantFunction
+    torch.manual_seed(0)
+    m = torchvision.models.mobilenet_v2(weights=None)
+    ws = [p.weight.data.cuda() for p in m.modules() if isinstance(p, (torch.nn.Conv2d, torch.nn.Linear))]
+    assert len(ws) == 53 and sum(w.numel() for w in ws) == 3469760 and sum(1 for w in ws if w.shape[1:] == (1, 3, 3)) == 17
+    cfgs = []
+    for w in ws:
+        cfg = LinearQuantizationConfig(symmetrical=True, quant_min=-128, quant_max=127, channel_axis=0, calibration='minmax')
+        ob = Observer(cfg); ob.observe(w); ob.render_quantization_config()
+        lo, hi = oracle.minmax_c(w.cpu().numpy(), 0)
+        want = np.float32([oracle.minmax_to_scale_offset(float(a), float(b), -128, 127, True)[0] for a, b in zip(lo, hi)])
+        assert np.array_equal(cfg.scale.cpu().numpy(), want), tuple(w.shape)
+        y = PPQuantFunction(w, cfg)
+        yo, qo = oracle.linear_quant_c(w.cpu().numpy(), want, np.zeros_like(want), 0, -128, 127, 0, return_int=True)
+        assert np.array_equal(bits(y), yo.view(np.uint32)), tuple(w.shape)
+        q = PPQLinearQuant_toInt(w, cfg)
+        assert q.dtype == torch.int8 and np.array_equal(q.cpu().numpy(), qo.astype(np.int8)), tuple(w.shape)
+        cfgs.append(cfg)
+    outs = MultiWeightQuantizer(ws, [c.scale for c in cfgs], [c.offset for c in cfgs])()
+    for w, c, y in zip(ws, cfgs, outs):
+        assert torch.equal(y, PPQuantFunction(w, c)), tuple(w.shape)
+
+
+def test_config4_fp8_bert_activations(ext, oracle):
+    """Config 4: FP8 E4M3 FloatingQuant on BERT-base activation shapes (bs 32, seq 512): hidden / FFN / attention probabilities, the observer's
+    power-of-two scale candidates, tie-rich (bf16-representable) values; oracle on a strided sample, full-size properties on the rest."""
+    from ppq_b200 import FloatingQuantizationConfig, QuantizationStates
+    from ppq_b200.observer import Observer
+    from ppq_b200.qfunction import PPQuantFunction
+    g = torch.Generator(device='cuda').manual_seed(4)
+    for shape, sigma in (((32, 512, 768), 1.0), ((32, 512, 3072), 8.0), ((32, 12, 512, 512), 1.0)):
+        x = torch.randn(shape, device='cuda', generator=g) * sigma
+        x.view(-1)[::5] = x.view(-1)[::5].bfloat16().float()                   # exact-tie candidates
+        for s in (1.0, 0.125, 4.0):
+            cfg = FloatingQuantizationConfig(exponent=4, mantissa=3, quant_min=-448.0, quant_max=448.0, power_of_2=True)
+            cfg.scale, cfg.offset, cfg.state = torch.tensor(s, device='cuda'), torch.tensor(0.0, device='cuda'), QuantizationStates.ACTIVATED
+            y = PPQuantFunction(x, cfg)
+            assert torch.equal(PPQuantFunction(y, cfg), y)                     # idempotent
+            assert float((y / s).abs().max()) <= 448.0
+            idx = torch.arange(0, x.numel(), 997, device='cuda')
+            want = oracle.float_quant_t(x.view(-1)[idx].cpu().numpy(), s, 0.0)
+            assert np.array_equal(bits(y.view(-1)[idx]), want.view(np.uint32)), (shape, s)
+    # the FP8 observers: constant (scale 1) and direct-MSE (7 power-of-two candidates)
+    x = torch.randn(32, 512, 768, device='cuda', generator=g) * 50
+    cfg = FloatingQuantizationConfig(calibration='constant')
+    ob = Observer(cfg); ob.observe(x); ob.render_quantization_config()
+    assert cfg.state == QuantizationStates.ACTIVATED and cfg.scale.item() == 1.0 and cfg.offset.item() == 0.0
+    cfg = FloatingQuantizationConfig(calibration='floating')
+    torch.manual_seed(1)
+    ob = Observer(cfg); ob.observe(x); ob.render_quantization_config()
+    assert cfg.scale.item() in ob.SCALE_CANDIDATES
+    # the chosen candidate minimises the fake-quant MSE over the whole tensor as well (sampled search, stable for this distribution)
+    losses = []
+    for s in ob.SCALE_CANDIDATES:
+        c2 = FloatingQuantizationConfig(); c2.scale, c2.offset, c2.state = torch.tensor(s, device='cuda'), torch.tensor(0.0, device='cuda'), QuantizationStates.ACTIVATED
+        losses.append(float(((PPQuantFunction(x, c2) - x) ** 2).mean()))
+    assert ob.SCALE_CANDIDATES[int(np.argmin(losses))] == cfg.scale.item()
+
+
+def test_config5_sharded_calibration_equals_single_run(ext):
+    """Config 5's shape of work (YOLOv5s-like activation set at 640x640, samples sharded over 8 ranks): emulate the 8 ranks one after the
+    other on one GPU, merge their arenas exactly as the two all-reduces do, and compare with the unsharded calibration bit for bit."""
+    from ppq_b200.calibration import ArenaCalibrator, pack_minmax_for_max_reduce, shard_indices, unpack_minmax_after_max_reduce
+    shapes = [(3, 640, 640), (32, 320, 320), (64, 160, 160), (128, 80, 80), (256, 40, 40), (512, 20, 20), (255, 80, 80), (255, 40, 40), (255, 20, 20)]
+    g = torch.Generator(device='cuda').manual_seed(5)
+    samples = [[(torch.randn((1,) + s, device='cuda', generator=g) * (1 + i % 3)).relu_() if k % 2 else torch.randn((1,) + s, device='cuda', generator=g)
+                for k, s in enumerate(shapes)] for i in range(16)]
+    T = len(shapes)
+    full = ArenaCalibrator(T, 'cuda')
+    for smp in samples: full.observe(smp)
+    full.end_phase()
+    for smp in samples: full.observe(smp)
+    full.end_phase()
+    R = 8
+    ranks = [ArenaCalibrator(T, 'cuda') for _ in range(R)]
+    for r, cal in enumerate(ranks):
+        for i in shard_indices(len(samples), r, R): cal.observe(samples[i])
+    packed = torch.stack([pack_minmax_for_max_reduce(c.minmax) for c in ranks]).amax(dim=0)       # == all_reduce(MAX)
+    for cal in ranks:
+        unpack_minmax_after_max_reduce(packed, cal.minmax); cal.end_phase()
+    assert all(torch.equal(c.minmax, full.minmax) and torch.equal(c.hist_scale, full.hist_scale) for c in ranks)
+    for r, cal in enumerate(ranks):
+        for i in shard_indices(len(samples), r, R): cal.observe(samples[i])
+    total = torch.stack([c.hist for c in ranks]).sum(dim=0, dtype=torch.int32)                   # == all_reduce(SUM)
+    assert torch.equal(total, full.hist)
+    for cal in ranks:
+        cal.hist.copy_(total); cal.end_phase()
+        assert torch.equal(cal.scale, full.scale) and torch.equal(cal.best_bin_range, full.best_bin_range)
+
+
+def test_dynamic_quantization_on_device(ext, oracle):
+    from ppq_b200 import LinearQuantizationConfig, QuantizationStates
+    from ppq_b200.qfunction import PPQuantFunction
+    g = torch.Generator(device='cuda').manual_seed(6)
+    x = torch.randn(8, 24, 56, 56, device='cuda', generator=g) * 2
+    cfg = LinearQuantizationConfig(symmetrical=False, dynamic=True, quant_min=0, quant_max=255)
+    cfg.state = QuantizationStates.ACTIVATED
+    y = PPQuantFunction(x, cfg)
+    lo, hi = oracle.minmax_t(x.cpu().numpy())
+    s, o = oracle.minmax_to_scale_offset(float(lo), float(hi), 0, 255, False)
+    assert np.array_equal(bits(y), oracle.linear_quant_t(x.cpu().numpy(), np.float32(s), np.float32(o), 0, 255).view(np.uint32))
+    cfg = LinearQuantizationConfig(symmetrical=True, dynamic=True, channel_axis=1)
+    cfg.state = QuantizationStates.ACTIVATED
+    y = PPQuantFunction(x, cfg)
+    lo, hi = oracle.minmax_c(x.cpu().numpy(), 1)
+    sc = np.float32([oracle.minmax_to_scale_offset(float(a), float(b), -128, 127, True)[0] for a, b in zip(lo, hi)])
+    assert np.array_equal(bits(y), oracle.linear_quant_c(x.cpu().numpy(), sc, np.zeros_like(sc), 1, -128, 127).view(np.uint32))
+
+
+def test_executor_calibration_paths_agree(ext):
+    """The module executor: hook-driven RuntimeCalibrationPass (one observer per tensor, the reference flow) and the arena calibrator (immediate
+    and deferred multi-tensor) give identical scales; weights are re-quantised per forward; baked weights equal the fake-quantised ones."""
+    import torchvision
+    from ppq_b200.calibration import RuntimeCalibrationPass
+    from ppq_b200.core import QuantizationStates
+    from ppq_b200.executor import TorchExecutor, calibrate_arena
+    torch.manual_seed(7)
+    data = [torch.rand(4, 3, 64, 64, device='cuda') for _ in range(8)]
+
+    def build():
+        torch.manual_seed(11)
+        ex = TorchExecutor(torchvision.models.resnet18(weights=None).cuda(), torch.zeros(2, 3, 64, 64, device='cuda'))
+        ex.quantize_parameters()
+        return ex
+    ex1 = build()
+    RuntimeCalibrationPass(method='kl').optimize(graph=ex1, dataloader=data, executor=ex1, calib_steps=8)
+    s1 = torch.stack([c.scale for c in ex1.observed_configs_all()])
+    ex2 = build()
+    cal = calibrate_arena(ex2, data, method='kl')
+    assert torch.equal(cal.scale, s1)
+    assert all(c.state == QuantizationStates.ACTIVATED for c in ex2.observed_configs_all())
+    # CUDA-graph replay of the whole forward (network + weight fake-quant + collectors): identical statistics
+    ex3 = build()
+    cal3 = calibrate_arena(ex3, data, method='kl', graphs=True)
+    assert torch.equal(cal3.minmax, cal.minmax) and torch.equal(cal3.hist, cal.hist) and torch.equal(cal3.scale, s1)
+    # quantised forward runs and differs from fp32 only by quantisation noise
+    x = data[0]
+    yq = ex2.forward(x)
+    for c in ex2.observed_configs_all(): c.state = QuantizationStates.FP32
+    for _, op in ex2.quantable_operations():
+        if op.weight_cfg is not None: op.weight_cfg.state = QuantizationStates.FP32
+    yf = ex2.forward(x)
+    snr = float(((yq - yf) ** 2).sum() / (yf ** 2).sum())
+    assert 0 < snr < 0.1                                                    # tests/test_block.py:35-40 bar: SNR(quantised vs fp32) < 0.1
