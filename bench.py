@@ -236,8 +236,14 @@ def run_ours(args, rank, world, local_rank):
     m_ms = sum(a.elapsed_time(b) for a, b in mm_events) / len(mm_events)
     hist_gbs = 4.0 * wl.act_elems / (h_ms * 1e-3) / 1e9
     mm_gbs = 4.0 * wl.act_elems / (m_ms * 1e-3) / 1e9
+    traffic = None
+    try:                                                                    # dram__bytes_read + dram__bytes_write of one launch, from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+        if tj.get('batch') == args.batch: traffic = tj['traffic_bytes_per_launch']
+    except Exception:
+        pass
     roofline = {'bound': 'hbm', 'kernel': 'multi_histogram_t_kernel', 'achieved': round(hist_gbs, 1), 'peak': peak, 'unit': 'GB/s',
-                'frac': round(hist_gbs / peak, 4), 'traffic': None, 'peak_source': peak_src, 'ms_per_launch': round(h_ms, 4),
+                'frac': round(hist_gbs / peak, 4), 'traffic': traffic, 'peak_source': peak_src, 'ms_per_launch': round(h_ms, 4),
                 'algorithmic_bytes_per_launch': 4 * wl.act_elems,
                 'other_kernels': {'multi_minmax_t_kernel': {'achieved': round(mm_gbs, 1), 'frac': round(mm_gbs / peak, 4), 'ms_per_launch': round(m_ms, 4)}}}
     result = {
@@ -290,6 +296,19 @@ def fakequant_sweep(ext, device, peak):
         out.append({'shape': 'x'.join(map(str, shape)), 'elems': n, 'us_per_call': round(us, 2), 'gelems_per_s': round(n / us / 1e3, 1),
                     'gbs': round(gbs, 1), 'frac_of_hbm_peak': round(gbs / peak, 4), 'distinct_buffers': nbuf})
         del xs, ys
+    # the executor's many small tensors, batched: 64 tensors of 1x512x28x28 (BASELINE config 1 shape) in ONE multi-tensor launch
+    from ppq_b200.calibration import MultiWeightQuantizer
+    xs = [torch.randn(1, 512, 28, 28, device=device) for _ in range(64 * 8)]
+    qs = [MultiWeightQuantizer(xs[i * 64:(i + 1) * 64], [s] * 64, [o] * 64, channel_axis=None) for i in range(8)]     # 8 x 103 MB: rotates past L2
+    for q in qs: q()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for r in range(40): qs[r % 8]()
+    b.record(); torch.cuda.synchronize()
+    us = a.elapsed_time(b) * 1e3 / 40
+    n = 64 * 512 * 28 * 28
+    out.append({'shape': '64 x (1x512x28x28) in one multi-tensor launch', 'elems': n, 'us_per_call': round(us, 2), 'gelems_per_s': round(n / us / 1e3, 1),
+                'gbs': round(8.0 * n / (us * 1e-6) / 1e9, 1), 'frac_of_hbm_peak': round(8.0 * n / (us * 1e-6) / 1e9 / peak, 4), 'distinct_buffers': 8})
     return out
 
 

@@ -249,7 +249,8 @@ class RuntimeCalibrationPass:
 
 
 class MultiWeightQuantizer:
-    """All per-channel weights of a network fake-quantised by ONE launch (Multi_QuantizeTensor_LC).  The executor re-quantises
+    """All per-channel weights of a network (or, with channel_axis=None, any list of per-tensor quantised tensors) fake-quantised by
+    ONE launch (Multi_QuantizeTensor_LC).  The executor re-quantises
     every Conv/Gemm weight on each forward until ParameterBakingPass freezes them (executor/torch.py:516-518); with ~54 small
     tensors per ResNet-50 forward that is launch-latency, not bandwidth -- one descriptor table turns it into one kernel."""
 
@@ -264,10 +265,13 @@ class MultiWeightQuantizer:
         self.offsets = [o.contiguous() for o in offsets]
         rows = []
         for w, y, s, o in zip(self.weights, self.outputs, self.scales, self.offsets):
-            axis = channel_axis % w.dim()
-            epc = 1
-            for d in w.shape[axis + 1:]: epc *= int(d)
-            C = int(w.shape[axis])
+            if channel_axis is None:                       # per-tensor: one channel spanning the whole tensor
+                epc, C = w.numel(), 1
+            else:
+                axis = channel_axis % w.dim()
+                epc = 1
+                for d in w.shape[axis + 1:]: epc *= int(d)
+                C = int(w.shape[axis])
             assert s.numel() == C and o.numel() == C
             rows.append([w.data_ptr(), y.data_ptr(), s.data_ptr(), o.data_ptr(), w.numel(), epc, C])
         self.max_n = max(r[4] for r in rows)

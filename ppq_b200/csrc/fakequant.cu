@@ -167,11 +167,20 @@ multi_channel_kernel(const ppq_b200_lc_desc *__restrict__ descs, int count, int 
             const uint32_t v0 = (uint32_t)(begin >> 2), v1 = (uint32_t)((begin + len) >> 2);
             const FastDiv32 de((uint32_t)(d.epc >> 2)), dc((uint32_t)d.C);
             const float4 *x4 = reinterpret_cast<const float4 *>(d.x);
-            for (uint32_t vi = v0 + threadIdx.x; vi < v1; vi += kThreads) {
-                const uint32_t row = de.quot(vi);
-                const uint32_t c = row - dc.quot(row) * (uint32_t)d.C;
-                const Op op(plan, __ldg(d.scale + c), __ldg(d.offset + c));
-                Emit<Op, float>::vec(op, ld_stream4(x4 + vi), d.y, (int64_t)vi);
+            for (uint32_t i = v0 + threadIdx.x; i < v1; i += kUnroll * kThreads) {
+                float4 v[kUnroll];
+#pragma unroll
+                for (int j = 0; j < kUnroll; j++) if (i + j * kThreads < v1) v[j] = ld_stream4(x4 + i + j * kThreads);
+#pragma unroll
+                for (int j = 0; j < kUnroll; j++) {
+                    const uint32_t vi = i + j * kThreads;
+                    if (vi < v1) {
+                        const uint32_t row = de.quot(vi);
+                        const uint32_t c = row - dc.quot(row) * (uint32_t)d.C;
+                        const Op op(plan, __ldg(d.scale + c), __ldg(d.offset + c));
+                        Emit<Op, float>::vec(op, v[j], d.y, (int64_t)vi);
+                    }
+                }
             }
         } else {
             // generic walk restricted to [begin, begin + len)
