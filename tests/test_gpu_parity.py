@@ -494,3 +494,42 @@ def test_full_size_properties(ext):
         h = torch.zeros(4096, dtype=torch.int32, device='cuda'); ext.Histogram_T(x, hs, True, h)
         inrange = (torch.floor(x.abs() / torch.tensor(hs, device='cuda', dtype=torch.float32)) <= 4095).sum().item()
         assert h.sum().item() == inrange and x.numel() - inrange <= 4
+
+
+# ------------------------------------------------------------------------------------------------ limits
+def test_maximum_size_and_too_many_elements(ext):
+    """The reference accepts numel <= 2^31 - 1 and throws beyond (linear.cu:108-109).  2^31 - 1 fp32 elements = 8.6 GB in + 8.6 GB out."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9: pytest.skip('needs ~26 GB of free HBM')
+    n = 2 ** 31 - 1
+    x = torch.empty(n, device='cuda').uniform_(-4, 4)
+    s, o = t1(0.031), t1(0)
+    y = ext.QuantizeTensor_LT(x, s, o, -128, 127, 0)
+    for sl in (slice(0, 1 << 20), slice(n - (1 << 20) - 3, n), slice(n // 2 - 5, n // 2 + (1 << 20))):      # head, ragged tail, middle
+        assert torch.equal(y[sl], ext.QuantizeTensor_LT(x[sl].clone(), s, o, -128, 127, 0))
+    mm = torch.empty(2, device='cuda'); ext.MinMax_Init(mm[0:1], mm[1:2]); ext.MinMax_T(x, mm)
+    assert mm[0].item() == x.min().item() and mm[1].item() == x.max().item()
+    h = torch.zeros(4096, dtype=torch.int32, device='cuda'); ext.Histogram_T(x, 4.0 / 4096, True, h)
+    assert h.sum().item() == n - int((torch.floor(x.abs() / torch.tensor(4.0 / 4096, device='cuda')) > 4095).sum().item())
+    del y
+    big = torch.empty(2 ** 31, device='cuda')
+    with pytest.raises(RuntimeError, match='too many element'):
+        ext.QuantizeTensor_LT(big, s, o, -128, 127, 0)
+    with pytest.raises(RuntimeError, match='too many element'):
+        ext.QuantizeTensor_LC(big.view(2, -1), torch.ones(2, device='cuda'), torch.zeros(2, device='cuda'), -128, 127, 0, 0)
+
+
+def test_histogram_many_bins_and_tiny_inputs(ext, oracle):
+    r = np.random.RandomState(61)
+    x = (r.standard_normal(300000) * 3).astype(np.float32)
+    for bins in (12287, 12288, 65536, 1):                       # shared-memory limit, global-atomic fallback, degenerate
+        hs = np.float32(12.0 / bins)
+        h = torch.zeros(bins, dtype=torch.int32, device='cuda')
+        ext.Histogram_T(dev(x), float(hs), True, h)
+        assert np.array_equal(h.cpu().numpy(), oracle.histogram_t(x, hs, bins, True)), bins
+    for n in (1, 2, 3, 4, 5, 31, 32, 33):                       # ragged tails around the vector / warp widths
+        xs = x[:n].copy()
+        h = torch.zeros(64, dtype=torch.int32, device='cuda'); ext.Histogram_T(dev(xs), 0.2, False, h)
+        assert np.array_equal(h.cpu().numpy(), oracle.histogram_t(xs, np.float32(0.2), 64, False)), n
+        y = ext.QuantizeTensor_LT(dev(xs), t1(0.1), t1(1), -8, 7, 0)
+        assert_bits_equal(y, oracle.linear_quant_t(xs, 0.1, 1, -8, 7, 0), f'tiny n={n}')
