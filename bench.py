@@ -269,8 +269,13 @@ def run_ours(args, rank, world, local_rank):
 
 
 def fakequant_sweep(ext, device, peak):
-    """LinearQuant_T INT8 over the north-star shape range.  Big shapes rotate over > L2 worth of distinct buffers; the small ones
-    are launch-latency bound and L2 resident by nature -- reported as latency."""
+    """LinearQuant_T INT8 over the north-star shape range (1x3x224x224 ... 1x2048x64x64, plus BERT-sized tensors).  Per shape:
+      us_per_call        the public op, eager (python -> binding -> at::empty_like -> kernel), what ppq.executor pays per fake-quant;
+      kernel_us / gbs    the kernel alone: the C-ABI launch captured in a CUDA graph over rotating input AND output buffers (> L2 in total
+                         for the large shapes), replayed back to back -- no host launch overhead, no allocator.
+    The small shapes are L2-resident and launch-latency bound by nature: their HBM fraction is reported but means latency."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, 'ppq_b200', '_lib', 'libppq_b200.so'))
     out = []
     s, o = torch.tensor([0.05], device=device), torch.tensor([0.0], device=device)
     for shape in ((1, 3, 224, 224), (1, 512, 28, 28), (1, 256, 56, 56), (1, 1024, 14, 14), (1, 2048, 64, 64), (32, 512, 768), (32, 12, 512, 512)):
@@ -278,24 +283,35 @@ def fakequant_sweep(ext, device, peak):
         nbuf = max(2, min(64, int(1.5e9 // (8 * n)) + 1))
         xs = [torch.randn(shape, device=device) for _ in range(nbuf)]
         ys = [torch.empty_like(x) for x in xs]
-        import ctypes
-        lib = ctypes.CDLL(os.path.join(ROOT, 'ppq_b200', '_lib', 'libppq_b200.so'))
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-        def launch(i):
-            lib.ppq_b200_linear_quant_t(ctypes.c_void_p(xs[i].data_ptr()), ctypes.c_void_p(ys[i].data_ptr()), ctypes.c_int64(n),
-                                        ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(o.data_ptr()), -128, 127, 0, st)
-        for i in range(nbuf): launch(i)
+        outs = [None] * nbuf
+        for i in range(nbuf): outs[i] = ext.QuantizeTensor_LT(xs[i], s, o, -128, 127, 0)
         reps = max(nbuf, 40)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); a.record()
-        for i in range(reps): launch(i % nbuf)
+        for i in range(reps): outs[i % nbuf] = ext.QuantizeTensor_LT(xs[i % nbuf], s, o, -128, 127, 0)
         b.record(); torch.cuda.synchronize()
-        us = a.elapsed_time(b) * 1e3 / reps
-        gbs = 8.0 * n / (us * 1e-6) / 1e9
-        out.append({'shape': 'x'.join(map(str, shape)), 'elems': n, 'us_per_call': round(us, 2), 'gelems_per_s': round(n / us / 1e3, 1),
-                    'gbs': round(gbs, 1), 'frac_of_hbm_peak': round(gbs / peak, 4), 'distinct_buffers': nbuf})
-        del xs, ys
+        op_us = a.elapsed_time(b) * 1e3 / reps
+        del outs
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+                for i in range(nbuf):
+                    lib.ppq_b200_linear_quant_t(ctypes.c_void_p(xs[i].data_ptr()), ctypes.c_void_p(ys[i].data_ptr()), ctypes.c_int64(n),
+                                                ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(o.data_ptr()), -128, 127, 0, st)
+        torch.cuda.current_stream(device).wait_stream(side)
+        g.replay(); torch.cuda.synchronize()
+        rounds = max(1, 64 // nbuf)
+        a.record()
+        for _ in range(rounds): g.replay()
+        b.record(); torch.cuda.synchronize()
+        k_us = a.elapsed_time(b) * 1e3 / (rounds * nbuf)
+        gbs = 8.0 * n / (k_us * 1e-6) / 1e9
+        out.append({'shape': 'x'.join(map(str, shape)), 'elems': n, 'us_per_call': round(op_us, 2), 'kernel_us': round(k_us, 2),
+                    'gelems_per_s': round(n / k_us / 1e3, 1), 'gbs': round(gbs, 1), 'frac_of_hbm_peak': round(gbs / peak, 4), 'distinct_buffers': nbuf})
+        del xs, ys, g
     # the executor's many small tensors, batched: 64 tensors of 1x512x28x28 (BASELINE config 1 shape) in ONE multi-tensor launch
     from ppq_b200.calibration import MultiWeightQuantizer
     xs = [torch.randn(1, 512, 28, 28, device=device) for _ in range(64 * 8)]
@@ -307,8 +323,9 @@ def fakequant_sweep(ext, device, peak):
     b.record(); torch.cuda.synchronize()
     us = a.elapsed_time(b) * 1e3 / 40
     n = 64 * 512 * 28 * 28
-    out.append({'shape': '64 x (1x512x28x28) in one multi-tensor launch', 'elems': n, 'us_per_call': round(us, 2), 'gelems_per_s': round(n / us / 1e3, 1),
-                'gbs': round(8.0 * n / (us * 1e-6) / 1e9, 1), 'frac_of_hbm_peak': round(8.0 * n / (us * 1e-6) / 1e9 / peak, 4), 'distinct_buffers': 8})
+    out.append({'shape': '64 x (1x512x28x28) in one multi-tensor launch', 'elems': n, 'us_per_call': round(us, 2), 'kernel_us': round(us, 2),
+                'gelems_per_s': round(n / us / 1e3, 1), 'gbs': round(8.0 * n / (us * 1e-6) / 1e9, 1),
+                'frac_of_hbm_peak': round(8.0 * n / (us * 1e-6) / 1e9 / peak, 4), 'distinct_buffers': 8})
     return out
 
 

@@ -47,23 +47,30 @@ constexpr int kUnroll = 4;          // independent 128-bit loads in flight per t
 // ---- per-tensor: one (scale, offset) for the whole tensor ---------------------------------------------------------------
 // VEC: x and y are 16-byte aligned -> float4 main loop + scalar tail; otherwise everything scalar.
 // Every round issues kUnroll predicated 128-bit loads before the first use, also in the ragged last round.
-template <class Op, class OutT, bool VEC>
-__global__ void __launch_bounds__(kThreads)
+template <class Op, class OutT, bool VEC, int U = kUnroll, int TPB = kThreads>
+__global__ void __launch_bounds__(TPB)
 ew_tensor_kernel(const float *__restrict__ x, OutT *__restrict__ y, int64_t n,
                  const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
     const typename Op::Plan plan(p);
     const Op op(plan, __ldg(scale), __ldg(offset));
-    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    const int64_t tid = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * TPB;
     if constexpr (VEC) {
         const int64_t n4 = n >> 2;
         const float4 *x4 = reinterpret_cast<const float4 *>(x);
-        for (int64_t i = tid; i < n4; i += kUnroll * stride) {
-            float4 v[kUnroll];
+        // Each warp walks contiguous segments of 32 x U vectors (lane-interleaved): the U loads of a thread hit one 2 KB span of
+        // HBM instead of U pages a grid-stride apart (measured +4 points of HBM peak on the per-channel twin of this loop).
+        constexpr int64_t kSeg = 32 * U;
+        const int64_t lane = threadIdx.x & 31;
+        const int64_t warp = tid >> 5, warps = stride >> 5;
+        const int64_t segs = (n4 + kSeg - 1) / kSeg;
+        for (int64_t sg = warp; sg < segs; sg += warps) {
+            const int64_t base = sg * kSeg + lane;
+            float4 v[U];
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) if (i + j * stride < n4) v[j] = ld_stream4(x4 + i + j * stride);
+            for (int j = 0; j < U; j++) if (base + j * 32 < n4) v[j] = ld_stream4(x4 + base + j * 32);
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) if (i + j * stride < n4) Emit<Op, OutT>::vec(op, v[j], y, i + j * stride);
+            for (int j = 0; j < U; j++) if (base + j * 32 < n4) Emit<Op, OutT>::vec(op, v[j], y, base + j * 32);
         }
         const int64_t t = (n4 << 2) + tid;                          // <= 3 leftover elements
         if (t < n) y[t] = Emit<Op, OutT>::one(op, x[t]);
@@ -94,6 +101,44 @@ __device__ __forceinline__ void channel_vec_body(const float *__restrict__ x, Ou
                 const uint32_t c = row - div_C.quot(row) * (uint32_t)C;
                 const Op op(plan, __ldg(scale + c), __ldg(offset + c));
                 Emit<Op, OutT>::vec(op, v[j], y, (int64_t)vi);
+            }
+        }
+    }
+}
+
+// Long rows (epc/4 >= 128): each warp walks contiguous 128-vector segments (lane-interleaved, 4 x 128-bit loads in flight per lane).
+// A segment touches at most two channel rows, so the operator is built once (twice when the segment straddles a row end, a
+// warp-uniform branch) per 16 elements of a thread instead of once per vector.
+template <class Op, class OutT>
+__global__ void __launch_bounds__(kThreads)
+ew_channel_seg_kernel(const float *__restrict__ x, OutT *__restrict__ y, uint32_t n4, int C, uint32_t epc4,
+                      FastDiv32 div_epc4, FastDiv32 div_C,
+                      const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
+    const typename Op::Plan plan(p);
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    constexpr uint32_t kSeg = 32 * kUnroll;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (kThreads / 32);
+    const uint32_t segs = (n4 + kSeg - 1) / kSeg;
+    for (uint32_t sg = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); sg < segs; sg += warps) {
+        const uint32_t base = sg * kSeg;
+        float4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) if (base + j * 32 + lane < n4) v[j] = ld_stream4(x4 + base + j * 32 + lane);
+        const uint32_t r0 = div_epc4.quot(base);
+        const uint32_t c0 = r0 - div_C.quot(r0) * (uint32_t)C;
+        const uint32_t next_row = (r0 + 1) * epc4;                   // first vector of the following row (no overflow: n4 < 2^29)
+        const Op op0(plan, __ldg(scale + c0), __ldg(offset + c0));
+        if (next_row >= base + kSeg) {                               // whole segment in one row (warp-uniform)
+#pragma unroll
+            for (int j = 0; j < kUnroll; j++) if (base + j * 32 + lane < n4) Emit<Op, OutT>::vec(op0, v[j], y, (int64_t)(base + j * 32 + lane));
+        } else {
+            const uint32_t c1 = (c0 + 1 == (uint32_t)C) ? 0u : c0 + 1;
+            const Op op1(plan, __ldg(scale + c1), __ldg(offset + c1));
+#pragma unroll
+            for (int j = 0; j < kUnroll; j++) {
+                const uint32_t vi = base + j * 32 + lane;
+                if (vi < n4) { if (vi < next_row) Emit<Op, OutT>::vec(op0, v[j], y, (int64_t)vi); else Emit<Op, OutT>::vec(op1, v[j], y, (int64_t)vi); }
             }
         }
     }
@@ -211,7 +256,7 @@ static int launch_tensor(const float *x, OutT *y, int64_t n, const float *scale,
                          typename Op::Params p, cudaStream_t st) {
     if (n <= 0 || !x || !y || !scale || !offset) return (int)cudaErrorInvalidValue;
     const bool vec = aligned16(x) && out_aligned<OutT>(y);
-    const int grid = grid_for(vec ? (n + 3) / 4 : n, kThreads, vec ? kUnroll : 4, 16);
+    const int grid = grid_for(vec ? (n + 3) / 4 : n, kThreads, vec ? kUnroll : 4, 8);       // persistent: 148 SMs x 8 CTAs
     if (vec) ew_tensor_kernel<Op, OutT, true><<<grid, kThreads, 0, st>>>(x, y, n, scale, offset, p);
     else     ew_tensor_kernel<Op, OutT, false><<<grid, kThreads, 0, st>>>(x, y, n, scale, offset, p);
     return (int)cudaGetLastError();
@@ -224,6 +269,12 @@ static int launch_channel(const float *x, OutT *y, int64_t n, int64_t epc, int C
     if (epc > 0x7fffffffLL || n % epc != 0) return (int)cudaErrorInvalidValue;
     if (epc % 4 == 0 && aligned16(x) && out_aligned<OutT>(y)) {
         const int64_t n4 = n / 4;
+        if (n4 <= 0x1fffffffLL && epc / 4 >= 128) {
+            const int grid = grid_for(n4, kThreads, kUnroll, 16);
+            ew_channel_seg_kernel<Op, OutT><<<grid, kThreads, 0, st>>>(x, y, (uint32_t)n4, C, (uint32_t)(epc / 4), FastDiv32((uint32_t)(epc / 4)),
+                                                                          FastDiv32((uint32_t)C), scale, offset, p);
+            return (int)cudaGetLastError();
+        }
         if (n4 <= 0x7fffffffLL) {
             const int grid = grid_for(n4, kThreads, kUnroll, 16);
             ew_channel_vec_kernel<Op, OutT><<<grid, kThreads, 0, st>>>(x, y, (uint32_t)n4, C, FastDiv32((uint32_t)(epc / 4)), FastDiv32((uint32_t)C),
@@ -273,8 +324,20 @@ int ppq_b200_linear_quant_t(const float *x, float *y, int64_t n, const float *sc
     cudaStream_t st = (cudaStream_t)stream;
     if (qmin > qmax) return (int)cudaErrorInvalidValue;
     if (rounding == RND_HALF_EVEN) {
-        if (variant_of(kVarLinearT) == 1 && n >= 4096 && aligned16(x) && aligned16(y))
+        const int var = variant_of(kVarLinearT);
+        if (var == 1 && n >= 4096 && aligned16(x) && aligned16(y))
             return launch_linear_quant_t_tma(x, y, n, scale, offset, qmin, qmax, st);
+        if (var >= 2 && n >= 4096 && aligned16(x) && aligned16(y)) {          // launch-shape experiments (tools/kbench.py)
+            using Op = LinearOp<0>;
+            const Op::Params p{qmin, qmax, 0};
+            const int64_t n4 = (n + 3) / 4;
+            if (var == 2) ew_tensor_kernel<Op, float, true, 8, 256><<<grid_for(n4, 256, 8, 16), 256, 0, st>>>(x, y, n, scale, offset, p);
+            else if (var == 3) ew_tensor_kernel<Op, float, true, 4, 512><<<grid_for(n4, 512, 4, 8), 512, 0, st>>>(x, y, n, scale, offset, p);
+            else if (var == 4) ew_tensor_kernel<Op, float, true, 2, 256><<<grid_for(n4, 256, 2, 32), 256, 0, st>>>(x, y, n, scale, offset, p);
+            else if (var == 5) ew_tensor_kernel<Op, float, true, 4, 128><<<grid_for(n4, 128, 4, 32), 128, 0, st>>>(x, y, n, scale, offset, p);
+            else ew_tensor_kernel<Op, float, true, 4, 256><<<grid_for(n4, 256, 4, 8), 256, 0, st>>>(x, y, n, scale, offset, p);   // 6: persistent 148x8
+            return (int)cudaGetLastError();
+        }
         return launch_tensor<LinearOp<0>, float>(x, y, n, scale, offset, {qmin, qmax, 0}, st);
     }
     return launch_tensor<LinearOp<-1>, float>(x, y, n, scale, offset, {qmin, qmax, rounding}, st);

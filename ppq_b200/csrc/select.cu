@@ -44,19 +44,20 @@ __global__ void select_init_kernel(SelectState *st, long long r0, long long r1) 
 template <int PASS>
 __global__ void __launch_bounds__(kSelThreads)
 select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restrict__ st) {
-    __shared__ int sh[2][kDigits];
-    for (int i = threadIdx.x; i < 2 * kDigits; i += kSelThreads) (&sh[0][0])[i] = 0;
+    __shared__ int sh[2][kDigits + 32];                            // + a trash slot per rank: the shared red is unconditional (cf. collectors.cu)
+    for (int i = threadIdx.x; i < 2 * (kDigits + 32); i += kSelThreads) (&sh[0][0])[i] = 0;
     __syncthreads();
     constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
     constexpr uint32_t dmask = PASS == 2 ? 0x3FFu : 0x7FFu;
     constexpr uint32_t pmask = PASS == 0 ? 0u : (PASS == 1 ? 0xFFE00000u : 0xFFFFFC00u);
     const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
     const bool same = (p0 == p1);
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(&sh[0][0]), a1 = (uint32_t)__cvta_generic_to_shared(&sh[1][0]);
     auto visit = [&](float v) {
         const uint32_t k = order_key(v);
         const uint32_t hi = k & pmask, d = (k >> shift) & dmask;
-        if (hi == p0) atomicAdd(&sh[0][d], 1);
-        if (!same && hi == p1) atomicAdd(&sh[1][d], 1);
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + ((hi == p0) ? d : (uint32_t)kDigits) * 4u) : "memory");
+        if (!same) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1 + ((hi == p1) ? d : (uint32_t)kDigits) * 4u) : "memory");
     };
     const int64_t first = (int64_t)blockIdx.x * kSelThreads + threadIdx.x, stride = (int64_t)gridDim.x * kSelThreads;
     if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
@@ -81,29 +82,39 @@ select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restri
     }
 }
 
-// One CTA: walk the digit histogram of each rank, pick the digit bucket that contains the rank, extend the prefix.
+// One 1024-thread CTA: block-wide prefix sum over the digit histogram of each rank (2 digits per thread, warp shuffles), pick the
+// digit bucket that contains the rank, extend the prefix, clear the histograms for the next pass.
 template <int PASS>
-__global__ void select_scan_kernel(SelectState *st, float *out, int out_stride) {
+__global__ void __launch_bounds__(1024) select_scan_kernel(SelectState *st, float *out, int out_stride) {
     constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
-    constexpr int digits = PASS == 2 ? 1024 : kDigits;
+    __shared__ unsigned long long warp_tot[32];
     __shared__ unsigned int new_prefix[2];
     __shared__ long long new_rank[2];
     const bool same = st->prefix[0] == st->prefix[1];
-    if (threadIdx.x < 2) {
-        const int r = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    for (int r = 0; r < 2; r++) {
         const unsigned long long *h = st->hist[(r == 1 && same) ? 0 : r];
-        long long k = st->rank[r];
-        int d = 0;
-        for (; d < digits - 1; d++) { const long long c = (long long)h[d]; if (k < c) break; k -= c; }
-        new_prefix[r] = st->prefix[r] | ((unsigned int)d << shift);
-        new_rank[r] = k;
+        const long long k = st->rank[r];
+        const unsigned long long c0 = h[2 * t], c1 = h[2 * t + 1];
+        unsigned long long incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+        if (lane == 31) warp_tot[w] = incl;
+        __syncthreads();
+        unsigned long long before = incl - (c0 + c1);
+        for (int i = 0; i < w; i++) before += warp_tot[i];
+        // the bucket d with  before(d) <= k < before(d) + count(d); ranks are always < total, so exactly one thread matches
+        if ((unsigned long long)k >= before && (unsigned long long)k < before + c0) { new_prefix[r] = st->prefix[r] | ((unsigned int)(2 * t) << shift); new_rank[r] = k - (long long)before; }
+        else if ((unsigned long long)k >= before + c0 && (unsigned long long)k < before + c0 + c1) {
+            new_prefix[r] = st->prefix[r] | ((unsigned int)(2 * t + 1) << shift); new_rank[r] = k - (long long)(before + c0);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * kDigits; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
-    if (threadIdx.x < 2) {
-        st->prefix[threadIdx.x] = new_prefix[threadIdx.x];
-        st->rank[threadIdx.x] = new_rank[threadIdx.x];
-        if (PASS == 2) out[threadIdx.x * out_stride] = key_to_float(new_prefix[threadIdx.x]);
+    for (int i = t; i < 2 * kDigits; i += 1024) (&st->hist[0][0])[i] = 0ull;
+    if (t < 2) {
+        st->prefix[t] = new_prefix[t];
+        st->rank[t] = new_rank[t];
+        if (PASS == 2) out[t * out_stride] = key_to_float(new_prefix[t]);
     }
 }
 

@@ -66,6 +66,15 @@ def main():
         report('histogram_asym_t randn', timeit(lambda i: ext.Histogram_Asymmetric_T(-5.0, 5.0, xs[i], True, h), args.reps, nbuf), 4)
         h2 = torch.zeros(2048, dtype=torch.int32, device=dev)
         report('histogram_t 2048 bins randn', timeit(lambda i: ext.Histogram_T(xs[i], hs * 2, True, h2), args.reps, nbuf), 4)
+    if 'ltshape' in only:
+        for shape_n in (8388608, 12582912, 802816):
+            xs2 = [torch.randn(shape_n, device=dev) for _ in range(max(2, int(1.5e9 // (8 * shape_n))))]
+            for var in (0, 5, 6):
+                ext.set_variant('linear_quant_t', var)
+                secs = timeit(lambda i: ext.QuantizeTensor_LT(xs2[i], one, zero, -128, 127, 0), 100, len(xs2))
+                print(f'LT n={shape_n} var{var}: {secs*1e6:8.2f} us  {8*shape_n/secs/1e9:8.1f} GB/s  {8*shape_n/secs/1e9/PEAK:6.1%}', flush=True)
+            ext.set_variant('linear_quant_t', 0)
+            del xs2
     if 'lt' in only:
         for var in (0, 1):
             ext.set_variant('linear_quant_t', var)
@@ -73,6 +82,8 @@ def main():
         ext.set_variant('linear_quant_t', 0)
         report('linear_quant_t mode1 (dyn rounding)', timeit(lambda i: ext.QuantizeTensor_LT(xs[i], one, zero, -128, 127, 1), args.reps, nbuf), 8)
         report('linear_quant_t toInt8', timeit(lambda i: ext.QuantizeTensor_toInt(xs[i], one, zero, -128, 127, -1000, 0, 8), args.reps, nbuf), 5)
+    if 'quantile' in only:
+        report('quantile_t q=0.9999 (3-pass radix select, 12 B/elem)', timeit(lambda i: ext.Quantile_T(xs[i], 0.9999), args.reps, nbuf), 12)
     if 'lc' in only:
         for shape, axis in (((n // 4608, 4608), 0), ((n // 512, 512), 0), ((n // 64, 64), 0), ((8, n // 8 // 3136, 3136), 1), ((n // 9, 9), 0), ((n // 768, 768), 1)):
             C = shape[axis]
