@@ -50,6 +50,26 @@ def allreduce_hist(hist: torch.Tensor, group=None) -> torch.Tensor:
     return hist
 
 
+def gather_in_sample_order(local: torch.Tensor, group=None) -> torch.Tensor:
+    """local: [T, n_local, 2] per-batch statistics of this rank (batch j of rank r is global batch r + j*R).  Returns [T, n_total, 2] in
+    global batch order on every rank (all-gather; ranks may hold n_local differing by one)."""
+    world = dist.get_world_size(group); rank = dist.get_rank(group)
+    n_local = torch.tensor([local.shape[1]], device=local.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    nmax = max(counts)
+    pad = torch.zeros(local.shape[0], nmax, local.shape[2], dtype=local.dtype, device=local.device)
+    pad[:, :local.shape[1]] = local
+    parts = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    rows = []
+    for j in range(nmax):
+        for r in range(world):
+            if j < counts[r]: rows.append(parts[r][:, j])
+    return torch.stack(rows, dim=1)
+
+
 def shard_indices(num_samples: int, rank: int, world_size: int) -> range:
     """Sample partition of SURVEY §8e: rank r takes samples r, r + R, r + 2R, ..."""
     return range(rank, num_samples, world_size)
@@ -206,10 +226,16 @@ class RuntimeCalibrationPass:
             if calib_step >= self._calib_steps: break
 
     def _reduce(self, phase: int):
-        from .observer import TorchHistObserver, TorchMinMaxObserver
+        from .observer import TorchHistObserver, TorchMinMaxObserver, TorchPercentileObserver
         obs = [ob for o in self._observers.values() for ob in o.hook._observer_table.values()]
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(self._group) > 1): return
         if phase == 1:
+            pct = [ob for ob in obs if isinstance(ob, TorchPercentileObserver) and ob._percentile_collector]
+            if pct:
+                # the percentile observer averages per-batch quantile pairs in fp32 (range.py:369): gather every rank's pairs and put
+                # them back in global sample order, so the mean is the same sum, in the same order, as the single-process run
+                merged = gather_in_sample_order(torch.stack([torch.cat(ob._percentile_collector, dim=0) for ob in pct]), self._group)
+                for ob, rows in zip(pct, merged): ob._percentile_collector = [rows]
             mm = [ob for ob in obs if isinstance(ob, TorchMinMaxObserver) and ob._slot is not None and ob._slot.cmins is None]
             if mm:
                 buf = torch.stack([ob._slot.minmax for ob in mm])

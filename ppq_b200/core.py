@@ -73,7 +73,18 @@ class QuantizationStates(Enum):
 
     @classmethod
     def is_activated(cls, state) -> bool:
-        return state in {QuantizationStates.ACTIVATED, QuantizationStates.PASSIVE}
+        # compared by name so that configs of the real `ppq` package (its own enum class) are understood too
+        return getattr(state, 'name', None) in ('ACTIVATED', 'PASSIVE')
+
+
+def state_is(config, name: str) -> bool:
+    """config.state == <name>, for our TensorQuantizationConfig and for the reference's (a different Enum class with the same names)."""
+    return getattr(config.state, 'name', None) == name
+
+
+def set_state(config, name: str) -> None:
+    """Assign the member `name` of whatever Enum class the config's state belongs to."""
+    config.state = type(config.state)[name]
 
 
 class TensorQuantizationConfig:

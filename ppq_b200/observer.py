@@ -17,7 +17,7 @@ import torch
 from .core import (OBSERVER_FLOATING_MSE_FETCHES, OBSERVER_KL_HIST_BINS, OBSERVER_KL_HIST_BINS_MANUL_OVERRIDE,
                    OBSERVER_MIN_SCALE, OBSERVER_MIN_SCALE_MANUL_OVERRIDE, OBSERVER_MSE_COMPUTE_INTERVAL,
                    OBSERVER_MSE_HIST_BINS, OBSERVER_PERCENTILE, OBSERVER_PERCENTILE_MANUL_OVERRIDE, QuantizationProperty,
-                   QuantizationStates, TensorQuantizationConfig)
+                   QuantizationStates, TensorQuantizationConfig, set_state, state_is)
 from .ffi import CUDA, CUDA_COMPLIER
 
 
@@ -107,7 +107,7 @@ class TorchMinMaxObserver(BaseTensorObserver):
     def observe(self, value: torch.Tensor):
         assert isinstance(value, torch.Tensor), 'TorchMinMaxObserver can only deal with torch Tensor values'
         assert value.numel() > 0, 'You are observing an empty tensor.'
-        if self._quant_cfg.state != QuantizationStates.INITIAL: return
+        if not state_is(self._quant_cfg, 'INITIAL'): return
         self._ensure_slot(value)
         if self._quant_cfg.policy.has_property(QuantizationProperty.PER_TENSOR):
             CUDA.MinMax_T(value, self._slot.minmax)
@@ -119,7 +119,7 @@ class TorchMinMaxObserver(BaseTensorObserver):
 
     def render_quantization_config(self):
         cfg = self._quant_cfg
-        if cfg.state != QuantizationStates.INITIAL: return
+        if not state_is(cfg, 'INITIAL'): return
         if self._observed == 0:
             raise ValueError('Can not render quantization config yet, Observer data collator is empty. '
                              'Invoke observe() function before render config.')
@@ -134,7 +134,7 @@ class TorchMinMaxObserver(BaseTensorObserver):
         else:
             cfg.scale, cfg.offset = _ext().MinMax_To_Scale_Offset(self._slot.cmins, self._slot.cmaxs, 1, cfg.quant_min, cfg.quant_max,
                                                                   sym, pow2, _min_scale(cfg))
-        cfg.state = QuantizationStates.ACTIVATED
+        set_state(cfg, 'ACTIVATED')
 
 
 class TorchHistObserver(TorchMinMaxObserver):
@@ -158,7 +158,7 @@ class TorchHistObserver(TorchMinMaxObserver):
         return self._slot.hist_scale
 
     def observe(self, value: torch.Tensor):
-        if self._quant_cfg.state != QuantizationStates.INITIAL: return
+        if not state_is(self._quant_cfg, 'INITIAL'): return
         assert value.numel() > 0, 'You are observing an empty tensor.'
         if self._phase == 'Detecting Minmax':
             return super().observe(value)
@@ -189,7 +189,7 @@ class TorchHistObserver(TorchMinMaxObserver):
 
     def render_quantization_config(self):
         cfg = self._quant_cfg
-        if cfg.state != QuantizationStates.INITIAL: return
+        if not state_is(cfg, 'INITIAL'): return
         if not cfg.policy.has_property(QuantizationProperty.PER_TENSOR):
             raise ValueError('Hist observer can only apply with per-tensor quantization config.')
         if self._phase == 'Detecting Minmax':
@@ -198,7 +198,7 @@ class TorchHistObserver(TorchMinMaxObserver):
             self._render_phase1()
         elif self._phase == 'Collating Hist':
             cfg.scale, cfg.offset = self.hist_to_scale_offset()
-            cfg.state = QuantizationStates.ACTIVATED
+            set_state(cfg, 'ACTIVATED')
 
 
 class TorchMSEObserver(TorchHistObserver):
@@ -243,7 +243,7 @@ class TorchPercentileObserver(BaseTensorObserver):
 
     @torch.no_grad()
     def observe(self, value: torch.Tensor):
-        if self._quant_cfg.state != QuantizationStates.INITIAL: return
+        if not state_is(self._quant_cfg, 'INITIAL'): return
         assert value is not None and value.numel() > 0, 'You are observing an empty tensor.'
         if self._quant_cfg.policy.has_property(QuantizationProperty.PER_TENSOR):
             self._percentile_collector.append(CUDA.Quantile(value, self._percentile).view(1, -1))
@@ -254,7 +254,7 @@ class TorchPercentileObserver(BaseTensorObserver):
 
     def render_quantization_config(self):
         cfg = self._quant_cfg
-        if cfg.state != QuantizationStates.INITIAL: return
+        if not state_is(cfg, 'INITIAL'): return
         if not cfg.policy.has_property(QuantizationProperty.PER_TENSOR):
             raise PermissionError('Percentile observer can not deal with per channel quantization.')
         if len(self._percentile_collector) == 0:
@@ -265,7 +265,7 @@ class TorchPercentileObserver(BaseTensorObserver):
                                                       cfg.policy.has_property(QuantizationProperty.SYMMETRICAL),
                                                       cfg.policy.has_property(QuantizationProperty.POWER_OF_2), _min_scale(cfg))
         cfg.scale, cfg.offset = scale.squeeze(0), offset.squeeze(0)
-        cfg.state = QuantizationStates.ACTIVATED
+        set_state(cfg, 'ACTIVATED')
 
 
 class ConstantObserver(BaseTensorObserver):
@@ -277,19 +277,20 @@ class ConstantObserver(BaseTensorObserver):
 
     @torch.no_grad()
     def observe(self, value: torch.Tensor):
-        if self._quant_cfg.state != QuantizationStates.INITIAL: return
+        if not state_is(self._quant_cfg, 'INITIAL'): return
         self._value_shape, self._value_device = value.shape, value.device
 
     def render_quantization_config(self):
         cfg = self._quant_cfg
-        if cfg.state != QuantizationStates.INITIAL: return
+        if not state_is(cfg, 'INITIAL'): return
         if not cfg.policy.has_property(QuantizationProperty.FLOATING):
             raise TypeError('This Observer is designed for floating quantization.')
         n = 1 if cfg.policy.has_property(QuantizationProperty.PER_TENSOR) else self._value_shape[cfg.channel_axis]
         scale = torch.ones(n, dtype=torch.float32, device=self._value_device)
         offset = torch.zeros(n, dtype=torch.float32, device=self._value_device)
         if cfg.policy.has_property(QuantizationProperty.PER_TENSOR): scale, offset = scale.squeeze(0), offset.squeeze(0)
-        cfg.scale, cfg.offset, cfg.state = scale, offset, QuantizationStates.ACTIVATED
+        cfg.scale, cfg.offset = scale, offset
+        set_state(cfg, 'ACTIVATED')
 
 
 class DirectMSEObserver(BaseTensorObserver):
@@ -308,7 +309,7 @@ class DirectMSEObserver(BaseTensorObserver):
     @torch.no_grad()
     def observe(self, value: torch.Tensor):
         cfg = self._quant_cfg
-        if cfg.state != QuantizationStates.INITIAL: return
+        if not state_is(cfg, 'INITIAL'): return
         if cfg.policy.has_property(QuantizationProperty.PER_CHANNEL):
             v = torch.transpose(value, 0, cfg.channel_axis).flatten(1)
             if not self._is_parameter:
@@ -323,10 +324,10 @@ class DirectMSEObserver(BaseTensorObserver):
     def render_quantization_config(self):
         from .qfunction import PPQuantFunction
         cfg = self._quant_cfg
-        if cfg.state != QuantizationStates.INITIAL: return
+        if not state_is(cfg, 'INITIAL'): return
         if not self._collector:
             raise PermissionError('Observer collector is empty, you should invoke observe function before render quantization config.')
-        cfg.state = QuantizationStates.ACTIVATED
+        set_state(cfg, 'ACTIVATED')
         per_channel = cfg.policy.has_property(QuantizationProperty.PER_CHANNEL)
         data = torch.cat(self._collector, dim=-1 if per_channel else 0).contiguous()
         n = data.shape[0] if per_channel else 1

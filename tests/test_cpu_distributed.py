@@ -39,7 +39,10 @@ def _worker(rank, world, port, out_dir):
             b = b[b <= bins - 1]
             hist[t] += torch.bincount(b, minlength=bins).int()
     allreduce_hist(hist)
-    torch.save({'minmax': minmax, 'hist': hist, 'mine': mine}, os.path.join(out_dir, f'r{rank}.pt'))
+    from ppq_b200.calibration import gather_in_sample_order
+    pairs = torch.stack([torch.stack([torch.stack([data[i][t].max(), data[i][t].min()]) for i in mine]) for t in range(T)])   # [T, n_local, 2]
+    ordered = gather_in_sample_order(pairs)
+    torch.save({'minmax': minmax, 'hist': hist, 'mine': mine, 'ordered': ordered}, os.path.join(out_dir, f'r{rank}.pt'))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -63,6 +66,9 @@ def test_sharded_statistics_equal_single_process(tmp_path):
             b = torch.floor(d[t].abs() / hs[t]).long(); b = b[b <= bins - 1]
             hist[t] += torch.bincount(b, minlength=bins).int()
     assert torch.equal(r0['hist'], hist)
+    want = torch.stack([torch.stack([torch.stack([d[t].max(), d[t].min()]) for d in data]) for t in range(T)])
+    assert torch.equal(r0['ordered'], want) and torch.equal(r1['ordered'], want)        # global sample order restored on every rank
+    assert torch.equal(r0['ordered'].mean(dim=1), want.mean(dim=1))                     # hence the fp32 mean is bit-identical
 
 
 def test_pack_unpack_minmax_and_shards():
