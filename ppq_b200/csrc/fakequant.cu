@@ -47,8 +47,8 @@ constexpr int kUnroll = 4;          // independent 128-bit loads in flight per t
 // ---- per-tensor: one (scale, offset) for the whole tensor ---------------------------------------------------------------
 // VEC: x and y are 16-byte aligned -> float4 main loop + scalar tail; otherwise everything scalar.
 // Every round issues kUnroll predicated 128-bit loads before the first use, also in the ragged last round.
-template <class Op, class OutT, bool VEC, int U = kUnroll, int TPB = kThreads>
-__global__ void __launch_bounds__(TPB)
+template <class Op, class OutT, bool VEC, int U = kUnroll, int TPB = kThreads, int MINB = 1>
+__global__ void __launch_bounds__(TPB, MINB)
 ew_tensor_kernel(const float *__restrict__ x, OutT *__restrict__ y, int64_t n,
                  const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
     const typename Op::Plan plan(p);
@@ -256,6 +256,12 @@ static int launch_tensor(const float *x, OutT *y, int64_t n, const float *scale,
                          typename Op::Params p, cudaStream_t st) {
     if (n <= 0 || !x || !y || !scale || !offset) return (int)cudaErrorInvalidValue;
     const bool vec = aligned16(x) && out_aligned<OutT>(y);
+    if (vec && n >= (int64_t)1 << 25) {
+        // >= 32 M elements: 8 loads in flight per thread (4 KB contiguous per warp) measured 92 % vs 89 % of HBM peak; below that the
+        // coarser work granularity costs more in the tail than the extra memory-level parallelism gains (82 % vs 71 % at 8 M elements)
+        ew_tensor_kernel<Op, OutT, true, 8><<<grid_for((n + 3) / 4, kThreads, 8, 16), kThreads, 0, st>>>(x, y, n, scale, offset, p);
+        return (int)cudaGetLastError();
+    }
     const int grid = grid_for(vec ? (n + 3) / 4 : n, kThreads, vec ? kUnroll : 4, 8);       // persistent: 148 SMs x 8 CTAs
     if (vec) ew_tensor_kernel<Op, OutT, true><<<grid, kThreads, 0, st>>>(x, y, n, scale, offset, p);
     else     ew_tensor_kernel<Op, OutT, false><<<grid, kThreads, 0, st>>>(x, y, n, scale, offset, p);
@@ -335,6 +341,12 @@ int ppq_b200_linear_quant_t(const float *x, float *y, int64_t n, const float *sc
             else if (var == 3) ew_tensor_kernel<Op, float, true, 4, 512><<<grid_for(n4, 512, 4, 8), 512, 0, st>>>(x, y, n, scale, offset, p);
             else if (var == 4) ew_tensor_kernel<Op, float, true, 2, 256><<<grid_for(n4, 256, 2, 32), 256, 0, st>>>(x, y, n, scale, offset, p);
             else if (var == 5) ew_tensor_kernel<Op, float, true, 4, 128><<<grid_for(n4, 128, 4, 32), 128, 0, st>>>(x, y, n, scale, offset, p);
+            else if (var == 9) ew_tensor_kernel<Op, float, true, 8, 256><<<grid_for(n4, 256, 8, 4), 256, 0, st>>>(x, y, n, scale, offset, p);
+            else if (var == 10) ew_tensor_kernel<Op, float, true, 8, 256><<<grid_for(n4, 256, 8, 8), 256, 0, st>>>(x, y, n, scale, offset, p);
+            else if (var == 11) ew_tensor_kernel<Op, float, true, 16, 256><<<grid_for(n4, 256, 16, 4), 256, 0, st>>>(x, y, n, scale, offset, p);
+            else if (var == 12) ew_tensor_kernel<Op, float, true, 8, 512><<<grid_for(n4, 512, 8, 2), 512, 0, st>>>(x, y, n, scale, offset, p);
+            else if (var == 7) ew_tensor_kernel<Op, float, true, 4, 256, 6><<<grid_for(n4, 256, 4, 12), 256, 0, st>>>(x, y, n, scale, offset, p);   // <= 42 regs, 6 CTAs/SM
+            else if (var == 8) ew_tensor_kernel<Op, float, true, 4, 256, 8><<<grid_for(n4, 256, 4, 16), 256, 0, st>>>(x, y, n, scale, offset, p);   // <= 32 regs, 8 CTAs/SM
             else ew_tensor_kernel<Op, float, true, 4, 256><<<grid_for(n4, 256, 4, 8), 256, 0, st>>>(x, y, n, scale, offset, p);   // 6: persistent 148x8
             return (int)cudaGetLastError();
         }

@@ -14,9 +14,9 @@ namespace ppqb {
 
 constexpr int kConsumers = 256;
 constexpr int kTmaThreads = kConsumers + 32;
-constexpr int kTileVec = 512;                   // float4 per tile  (8 KB)
+constexpr int kTileVec = 1024;                  // float4 per tile  (16 KB)
 constexpr int kTileBytes = kTileVec * 16;
-constexpr int kStages = 6;                      // 48 KB of shared memory per CTA -> 4 CTAs / SM
+constexpr int kStages = 4;                      // 64 KB of shared memory per CTA -> 3 CTAs / SM, 192 KB of tiles in flight per SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -88,13 +88,15 @@ linear_quant_t_tma_kernel(const float *__restrict__ x, float *__restrict__ y, in
                 mbar_wait(done + s, ph);                                          // tile k quantised in shared memory
                 tma_store_1d(reinterpret_cast<float4 *>(y) + t * kTileVec, tiles + s * kTileVec, tile_bytes(k));
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                if (k + kStages < my_tiles) {
-                    // the slot can be refilled once the store has finished READING shared memory
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    const int64_t k2 = k + kStages;
+                // Refill the slot of the PREVIOUS tile: its store was committed one iteration ago, so waiting for "all but the newest
+                // store have finished reading shared memory" does not stall on the store just issued.
+                if (k >= 1 && (k - 1) + kStages < my_tiles) {
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    const int64_t k2 = (k - 1) + kStages;
+                    const int s2 = (int)((k - 1) % kStages);
                     const int64_t t2 = blockIdx.x + k2 * (int64_t)gridDim.x;
-                    mbar_expect_tx(full + s, tile_bytes(k2));
-                    tma_load_1d(tiles + s * kTileVec, reinterpret_cast<const float4 *>(x) + t2 * kTileVec, tile_bytes(k2), full + s);
+                    mbar_expect_tx(full + s2, tile_bytes(k2));
+                    tma_load_1d(tiles + s2 * kTileVec, reinterpret_cast<const float4 *>(x) + t2 * kTileVec, tile_bytes(k2), full + s2);
                 }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");           // all stores complete before exit
@@ -141,7 +143,7 @@ int launch_linear_quant_t_tma(const float *x, float *y, int64_t n, const float *
     }
     const int64_t n4 = n >> 2;
     const int64_t tiles = (n4 + kTileVec - 1) / kTileVec;
-    int64_t grid = (int64_t)kSMs * 4;
+    int64_t grid = (int64_t)kSMs * 3;
     if (grid > tiles) grid = tiles;
     if (grid < 1) grid = 1;
     linear_quant_t_tma_kernel<<<(int)grid, kTmaThreads, smem, st>>>(x, y, n, scale, offset, qmin, qmax);
