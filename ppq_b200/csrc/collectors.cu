@@ -70,12 +70,18 @@ __device__ __forceinline__ void stream_elements(const float *__restrict__ x, int
     if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
         const int64_t n4 = n >> 2;
         const float4 *x4 = reinterpret_cast<const float4 *>(x);
-        for (int64_t i = first; i < n4; i += kUnroll * stride) {      // kUnroll predicated loads in flight, also in the ragged round
+        // warp-contiguous segments of 32 x kUnroll vectors (lane-interleaved): a thread's kUnroll loads in flight fall into one 2 KB
+        // span of HBM (same pattern as the fake-quant kernels, where it measured +3..4 points of HBM peak over grid-stride)
+        constexpr int64_t kSeg = 32 * kUnroll;
+        const int64_t lane = first & 31, warp = first >> 5, warps = stride >> 5;
+        const int64_t segs = (n4 + kSeg - 1) / kSeg;
+        for (int64_t sg = warp; sg < segs; sg += warps) {
+            const int64_t base = sg * kSeg + lane;
             float4 v[kUnroll];
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) if (i + j * stride < n4) v[j] = ld_stream4(x4 + i + j * stride);
+            for (int j = 0; j < kUnroll; j++) if (base + j * 32 < n4) v[j] = ld_stream4(x4 + base + j * 32);
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) if (i + j * stride < n4) { f(v[j].x); f(v[j].y); f(v[j].z); f(v[j].w); }
+            for (int j = 0; j < kUnroll; j++) if (base + j * 32 < n4) { f(v[j].x); f(v[j].y); f(v[j].z); f(v[j].w); }
         }
         const int64_t t = (n4 << 2) + first;
         if (t < n) f(x[t]);
