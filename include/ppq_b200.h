@@ -163,6 +163,12 @@ PPQ_B200_API int ppq_b200_kl_search(const int32_t *hist_arena, int64_t count, in
 /* replaces compute_mse_loss, ppq/csrc/cpu/hist_mse.cc:3-28 (ffi.py:263-270).  HOST function on HOST memory, exactly
  * like the reference's (it is a serial fp32 accumulation over <= 2048 bins). */
 PPQ_B200_API float ppq_b200_compute_mse_loss(const int64_t *hist, int64_t nbins, int start, int step, int end);
+/* Device MSE grid search: TorchMSEObserver.hist_to_scale_offset (range.py:456-520) over `count` histograms in one launch; each
+ * candidate's loss is the bit-exact serial fp32 accumulation of compute_mse_loss.  minmax_arena: {min,max} per histogram. */
+PPQ_B200_API int ppq_b200_mse_search(const int32_t *hist_arena, int64_t count, int64_t bins, const float *minmax_arena,
+                                     int qmin, int qmax, int symmetrical, int power_of_2, double min_scale, int interval,
+                                     float *scale_out, float *offset_out, void *stream);
+
 /* ---- training-pass helpers that share the scalar quantizer ("next" rows) ---------------------------- */
 /* replaces QuantizeTensor_LT_B, linear.cu:235-324: grad_x (STE with clip mask) and grad_s (1 float; zeroed here). */
 PPQ_B200_API int ppq_b200_linear_quant_t_backward(const float *x, const float *dy, int64_t n,

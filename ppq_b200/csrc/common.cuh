@@ -152,18 +152,7 @@ struct FastDiv32 {
     }
 };
 
-// ---- warp / block reductions ----------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_min(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
+// ---- atomics --------------------------------------------------------------------------------------------------------------
 // Float atomic min/max on raw IEEE bits (works for mixed signs; see DESIGN.md "statistics arena").
 // NaN is encoded by the caller: for the max slot +NaN (0x7FC00000) wins every signed-int max; for the min slot
 // -NaN (0xFFC00000) wins every unsigned max among negatives and is below every positive as a signed int.

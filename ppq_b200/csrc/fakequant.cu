@@ -333,21 +333,12 @@ int ppq_b200_linear_quant_t(const float *x, float *y, int64_t n, const float *sc
         const int var = variant_of(kVarLinearT);
         if (var == 1 && n >= 4096 && aligned16(x) && aligned16(y))
             return launch_linear_quant_t_tma(x, y, n, scale, offset, qmin, qmax, st);
-        if (var >= 2 && n >= 4096 && aligned16(x) && aligned16(y)) {          // launch-shape experiments (tools/kbench.py)
+        if (var >= 2 && n >= 4096 && aligned16(x) && aligned16(y)) {          // launch-shape A/B knobs (tools/kbench.py; results in DESIGN.md)
             using Op = LinearOp<0>;
             const Op::Params p{qmin, qmax, 0};
             const int64_t n4 = (n + 3) / 4;
-            if (var == 2) ew_tensor_kernel<Op, float, true, 8, 256><<<grid_for(n4, 256, 8, 16), 256, 0, st>>>(x, y, n, scale, offset, p);
-            else if (var == 3) ew_tensor_kernel<Op, float, true, 4, 512><<<grid_for(n4, 512, 4, 8), 512, 0, st>>>(x, y, n, scale, offset, p);
-            else if (var == 4) ew_tensor_kernel<Op, float, true, 2, 256><<<grid_for(n4, 256, 2, 32), 256, 0, st>>>(x, y, n, scale, offset, p);
-            else if (var == 5) ew_tensor_kernel<Op, float, true, 4, 128><<<grid_for(n4, 128, 4, 32), 128, 0, st>>>(x, y, n, scale, offset, p);
-            else if (var == 9) ew_tensor_kernel<Op, float, true, 8, 256><<<grid_for(n4, 256, 8, 4), 256, 0, st>>>(x, y, n, scale, offset, p);
-            else if (var == 10) ew_tensor_kernel<Op, float, true, 8, 256><<<grid_for(n4, 256, 8, 8), 256, 0, st>>>(x, y, n, scale, offset, p);
-            else if (var == 11) ew_tensor_kernel<Op, float, true, 16, 256><<<grid_for(n4, 256, 16, 4), 256, 0, st>>>(x, y, n, scale, offset, p);
-            else if (var == 12) ew_tensor_kernel<Op, float, true, 8, 512><<<grid_for(n4, 512, 8, 2), 512, 0, st>>>(x, y, n, scale, offset, p);
-            else if (var == 7) ew_tensor_kernel<Op, float, true, 4, 256, 6><<<grid_for(n4, 256, 4, 12), 256, 0, st>>>(x, y, n, scale, offset, p);   // <= 42 regs, 6 CTAs/SM
-            else if (var == 8) ew_tensor_kernel<Op, float, true, 4, 256, 8><<<grid_for(n4, 256, 4, 16), 256, 0, st>>>(x, y, n, scale, offset, p);   // <= 32 regs, 8 CTAs/SM
-            else ew_tensor_kernel<Op, float, true, 4, 256><<<grid_for(n4, 256, 4, 8), 256, 0, st>>>(x, y, n, scale, offset, p);   // 6: persistent 148x8
+            if (var == 2) ew_tensor_kernel<Op, float, true, 8, 256><<<grid_for(n4, 256, 8, 16), 256, 0, st>>>(x, y, n, scale, offset, p);      // 8 loads in flight
+            else ew_tensor_kernel<Op, float, true, 4, 256><<<grid_for(n4, 256, 4, 8), 256, 0, st>>>(x, y, n, scale, offset, p);                 // 4 loads, persistent
             return (int)cudaGetLastError();
         }
         return launch_tensor<LinearOp<0>, float>(x, y, n, scale, offset, {qmin, qmax, 0}, st);

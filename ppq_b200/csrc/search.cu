@@ -182,6 +182,82 @@ kl_search_kernel(const int32_t *__restrict__ hist_arena, int bins, const float *
     }
 }
 
+// ---- MSE search: one CTA per histogram, one thread per candidate grid ----------------------------------------------------------
+// TorchMSEObserver.hist_to_scale_offset (range.py:456-520) drives compute_mse_loss (hist_mse.cc:3-28) over candidate (start, step)
+// grids.  The loss of a candidate is a SERIAL fp32 accumulation over the bins; each thread reproduces that order exactly, so every
+// candidate's loss is bit-identical to the host function and the first minimum in enumeration order wins, as with python's stable sort.
+constexpr int kMseThreads = 1024;
+
+__device__ __forceinline__ float mse_loss_of(const float *__restrict__ h, int bins, float ftotal, int start, int step, int end) {
+    float loss = 0.f;
+    for (int idx = 0; idx < bins; idx++) {
+        float err;
+        if (idx < start) err = (float)((double)(start - idx - 1) + 0.5);
+        else if (idx > end) err = (float)((double)(idx - end) + 0.5);
+        else {
+            const int l = (idx - start) % step, r = step - l - 1;
+            if (l == r) err = (float)((double)l + 0.25);
+            else { const float le = (float)((double)l + 0.5), re = (float)((double)r + 0.5); err = le < re ? le : re; }
+        }
+        loss = __fadd_rn(loss, __fdiv_rn(__fmul_rn(__fmul_rn(h[idx], err), err), ftotal));
+    }
+    return loss;
+}
+
+__global__ void __launch_bounds__(kMseThreads)
+mse_search_kernel(const int32_t *__restrict__ hist_arena, int bins, const float *__restrict__ minmax_arena, int qmin, int qmax, int sym,
+                  int pow2, double min_scale, int interval, float *__restrict__ scale_out, float *__restrict__ offset_out) {
+    extern __shared__ float mh[];                                      // [bins] counts as fp32 (int64 -> float upstream; same value)
+    __shared__ long long s_total;
+    __shared__ float best_loss[kMseThreads / 32];
+    __shared__ int best_idx[kMseThreads / 32];
+    const int32_t *hist = hist_arena + (int64_t)blockIdx.x * bins;
+    if (threadIdx.x == 0) { long long t = 0; for (int i = 0; i < bins; i++) t += hist[i]; s_total = t; }
+    for (int i = threadIdx.x; i < bins; i += kMseThreads) mh[i] = (float)hist[i];
+    __syncthreads();
+    const float ftotal = (float)s_total;
+    const double vmin = (double)minmax_arena[2 * blockIdx.x], vmax = (double)minmax_arena[2 * blockIdx.x + 1];
+    const double hs = (sym ? fmax(fabs(vmax), fabs(vmin)) : (vmax - vmin)) / (double)bins;      // python doubles, range.py:294-300
+    const int levels = (qmax - qmin) + 1;
+    const int S = bins / levels;                                       // steps 1..S
+    // candidate enumeration, in the reference's order: 0 = the min-max fallback (start 0, step S+1); then (start_i, step) row-major
+    int nstarts = 1;
+    if (!sym) { nstarts = 0; for (int st = 0; st < bins; st += interval) { if ((double)st * hs + vmin > 0.0) break; nstarts++; } }
+    const int ncand = 1 + nstarts * S;
+    float my_loss = __int_as_float(0x7F800000); int my_idx = 0x7fffffff;
+    for (int c = threadIdx.x; c < ncand; c += kMseThreads) {
+        int start, step, end; bool valid = true;
+        if (c == 0) { start = 0; step = S + 1; end = levels * step; }
+        else {
+            const int si = (c - 1) / S; step = (c - 1) % S + 1; start = sym ? 0 : si * interval; end = start + levels * step;
+            if (end > bins + levels) valid = false;                    // the reference `break`s the step loop here: larger steps are invalid too
+        }
+        if (!valid) continue;
+        const float loss = mse_loss_of(mh, bins, ftotal, start, step, end);
+        if (loss < my_loss || (loss == my_loss && c < my_idx)) { my_loss = loss; my_idx = c; }
+    }
+    // block arg-min, ties to the lowest candidate index
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ol = __shfl_xor_sync(0xffffffffu, my_loss, o); const int oi = __shfl_xor_sync(0xffffffffu, my_idx, o);
+        if (ol < my_loss || (ol == my_loss && oi < my_idx)) { my_loss = ol; my_idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { best_loss[threadIdx.x >> 5] = my_loss; best_idx[threadIdx.x >> 5] = my_idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float bl = best_loss[0]; int bi = best_idx[0];
+        for (int w = 1; w < kMseThreads / 32; w++) if (best_loss[w] < bl || (best_loss[w] == bl && best_idx[w] < bi)) { bl = best_loss[w]; bi = best_idx[w]; }
+        int start, step;
+        if (bi == 0) { start = 0; step = S + 1; } else { start = sym ? 0 : ((bi - 1) / S) * interval; step = (bi - 1) % S + 1; }
+        const int end = start + levels * step;
+        const double lo = sym ? -((double)end * hs) : (double)start * hs + vmin;
+        const double hi = sym ? ((double)end * hs) : (double)end * hs + vmin;
+        const ScaleOffset r = minmax_to_scale_offset_dev(lo, hi, qmin, qmax, sym != 0, pow2 != 0, min_scale);
+        scale_out[blockIdx.x] = (float)r.scale;
+        offset_out[blockIdx.x] = (float)r.offset;
+    }
+}
+
 }  // namespace ppqb
 
 using namespace ppqb;
@@ -218,6 +294,17 @@ int ppq_b200_kl_search(const int32_t *hist_arena, int64_t count, int64_t bins, c
     }
     kl_search_kernel<<<(int)count, kKlThreads, smem, (cudaStream_t)stream>>>(hist_arena, (int)bins, hist_scale_arena, minmax_arena,
                                                                                num_of_bits, power_of_2, min_scale, scale_out, best_bin_range_out);
+    return (int)cudaGetLastError();
+}
+
+int ppq_b200_mse_search(const int32_t *hist_arena, int64_t count, int64_t bins, const float *minmax_arena, int qmin, int qmax,
+                        int symmetrical, int power_of_2, double min_scale, int interval, float *scale_out, float *offset_out, void *stream) {
+    if (count <= 0 || count > 0x7fffffffLL || !hist_arena || !minmax_arena || !scale_out || !offset_out || qmax <= qmin || interval <= 0)
+        return (int)cudaErrorInvalidValue;
+    const int64_t levels = (int64_t)qmax - qmin + 1;
+    if (bins < levels || bins > 11264) return (int)cudaErrorInvalidValue;       // at least one step; fp32 copy of the bins within 44 KB of smem
+    mse_search_kernel<<<(int)count, kMseThreads, (size_t)bins * sizeof(float), (cudaStream_t)stream>>>(
+        hist_arena, (int)bins, minmax_arena, qmin, qmax, symmetrical, power_of_2, min_scale, interval, scale_out, offset_out);
     return (int)cudaGetLastError();
 }
 

@@ -272,6 +272,17 @@ void Multi_QuantizeTensor_LC(const Tensor &descs, const int64_t max_numel, const
     CheckStatus(ppq_b200_multi_linear_quant_c(reinterpret_cast<const ppq_b200_lc_desc *>(descs.data_ptr<int64_t>()), (int)descs.size(0), max_numel,
                                               clip_min, clip_max, rounding, Stream()), "Multi_QuantizeTensor_LC");
 }
+std::vector<Tensor> MSE_Search(const Tensor &hist_arena, const int64_t bins, const Tensor &minmax_arena, const int quant_min, const int quant_max,
+                               const bool symmetrical, const bool power_of_2, const double min_scale, const int interval) {
+    CheckTensor(hist_arena, at::kInt, "HistArena(Expect to be INT32)");
+    CheckTensor(minmax_arena, at::kFloat, "MinMaxArena(Expect to be FP32)");
+    const c10::cuda::CUDAGuard guard(hist_arena.device());
+    const int64_t count = hist_arena.numel() / bins;
+    Tensor scale = at::empty({count}, minmax_arena.options()), offset = at::empty({count}, minmax_arena.options());
+    CheckStatus(ppq_b200_mse_search(hist_arena.data_ptr<int>(), count, bins, F(minmax_arena), quant_min, quant_max, symmetrical, power_of_2,
+                                    min_scale, interval, scale.data_ptr<float>(), offset.data_ptr<float>(), Stream()), "MSE_Search");
+    return {scale, offset};
+}
 int set_variant(const std::string &kernel, int variant) { return ppq_b200_set_variant(kernel.c_str(), variant); }
 int get_variant(const std::string &kernel) { return ppq_b200_get_variant(kernel.c_str()); }
 
@@ -303,6 +314,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("MinMax_To_Scale_Offset", MinMax_To_Scale_Offset, "MinMax_To_Scale_Offset");
     m.def("Hist_Scale_From_MinMax", Hist_Scale_From_MinMax, "Hist_Scale_From_MinMax");
     m.def("KL_Search", KL_Search, "KL_Search");
+    m.def("MSE_Search", MSE_Search, "MSE_Search");
     m.def("set_variant", set_variant, "set_variant");
     m.def("get_variant", get_variant, "get_variant");
     m.def("abi_version", ppq_b200_abi_version, "abi_version");

@@ -1,4 +1,8 @@
 // variants.h -- run-time kernel variant selection (profiling / A-B benchmarking knob, see ppq_b200_set_variant).
+//   "linear_quant_t": 0 default (LDG.128, warp-contiguous segments, unroll by size) | 1 TMA-staged smem ring | 2 force 8 loads in flight
+//                     | 3 force 4 loads in flight on a persistent 148 x 8 grid
+//   "histogram":      0 default (1024-thr CTA per SM, unconditional red.shared + trash slot) | 1 generic-pointer atomicAdd
+//                     | 2 __match_any_sync aggregation | 3 global atomics like the reference | 4 the first layout (256-thr CTAs x 8 per SM)
 #pragma once
 namespace ppqb {
 enum { kVarLinearT = 0, kVarHistogram = 1, kVarMinMax = 2, kVarCount = 8 };

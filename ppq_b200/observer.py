@@ -216,21 +216,16 @@ class TorchMSEObserver(TorchHistObserver):
             self._min, self._max = (float(v) for v in self._slot.minmax.tolist())
 
     def hist_to_scale_offset(self):
-        from .search import mse_search_host
+        """Device grid search (MSE_Search): every candidate's loss is the bit-exact serial fp32 accumulation of compute_mse_loss, the first
+        minimum wins like python's stable sort, the winning range goes through minmax_to_scale_offset in fp64 -- no histogram D2H, no host loop.
+        `ppq_b200.search.mse_search_host` keeps the reference's host formulation (CUDA.compute_mse_loss per candidate) for cross-checking."""
         cfg = self._quant_cfg
         if cfg.policy.has_property(QuantizationProperty.PER_CHANNEL):
             raise PermissionError('Torch Mse observer do not support PER_CHANNEL policy now, please wait.')
-        hist = self._slot.hist.cpu().tolist()
-        hist_scale = float(self._slot.hist_scale.item())
-        # the reference keeps hist_scale as a Python double (range.py:300); recompute it the same way from min / max
-        sym = cfg.policy.has_property(QuantizationProperty.SYMMETRICAL)
-        hist_range = float(max(abs(self._max), abs(self._min))) if sym else self._max - self._min
-        hist_scale = hist_range / self._hist_bins
-        scale, offset = mse_search_host(hist, hist_scale, self._min, cfg.quant_min, cfg.quant_max, sym,
-                                        cfg.policy.has_property(QuantizationProperty.POWER_OF_2), _min_scale(cfg))
-        dev = self._slot.hist.device
-        return (torch.tensor([scale], dtype=torch.float32, device=dev).squeeze(0),
-                torch.tensor([offset], dtype=torch.float32, device=dev).squeeze(0))
+        scale, offset = _ext().MSE_Search(self._slot.hist.view(1, -1), self._hist_bins, self._slot.minmax,
+                                          cfg.quant_min, cfg.quant_max, cfg.policy.has_property(QuantizationProperty.SYMMETRICAL),
+                                          cfg.policy.has_property(QuantizationProperty.POWER_OF_2), _min_scale(cfg), OBSERVER_MSE_COMPUTE_INTERVAL)
+        return scale.squeeze(0), offset.squeeze(0)
 
 
 class TorchPercentileObserver(BaseTensorObserver):

@@ -405,6 +405,33 @@ def test_kl_search_kernel_vs_reference(ext):
             assert scale[i].item() == np.float32((want_best / 4096) * float(np.float32(c['hist_scale'])) * (4096 / qb)), c
 
 
+def test_mse_search_kernel_vs_host_search(ext, oracle):
+    """Device MSE grid search == the host search over the native compute_mse_loss (the reference's USING_CUDA_KERNEL=True flow), sym and asym,
+    on the reference-generated histograms and on random ones; ties resolved to the first candidate like python's stable sort."""
+    from ppq_b200.search import mse_search_host
+    g = load_golden('hist_search.npz')
+    hists, mms, want = [], [], []
+    for c in cases_of(g, 'mse_cases'):
+        hists.append(g[f"mse_hist{c['j']}"]); mms.append((np.float32(c['vmin']), np.float32(c['vmax']))); want.append(c)
+    r = np.random.RandomState(8)
+    for j in range(6):
+        h = (r.gamma(0.6, 300.0, size=2048) * (r.rand(2048) > 0.3)).astype(np.int32)
+        if j == 5: h[:] = 7                                   # flat histogram: many tied candidates
+        lo, hi = np.float32(-r.rand() * 3 - 0.1), np.float32(r.rand() * 5 + 0.1)
+        hists.append(h); mms.append((lo, hi)); want.append(None)
+    H = torch.tensor(np.stack(hists), dtype=torch.int32, device='cuda')
+    MM = torch.tensor(np.array(mms, np.float32), device='cuda')
+    for sym in (True, False):
+        qmin, qmax = (-128, 127) if sym else (0, 255)
+        s, o = ext.MSE_Search(H, 2048, MM, qmin, qmax, sym, False, 1e-8, 8)
+        for i, (h, (lo, hi)) in enumerate(zip(hists, mms)):
+            hs = (max(abs(float(lo)), abs(float(hi))) if sym else (float(hi) - float(lo))) / 2048
+            ws, wo = mse_search_host(h.tolist(), hs, float(lo), qmin, qmax, sym, False, 1e-8)
+            assert s[i].item() == np.float32(ws) and o[i].item() == np.float32(wo), (sym, i, s[i].item(), ws)
+            os_, oo = oracle.mse_search(h, hs, float(lo), qmin, qmax, sym)
+            assert np.float32(os_) == np.float32(ws) and float(oo) == float(wo)
+
+
 def test_observers_end_to_end_vs_reference(ext, oracle):
     """Same data (seeded) through ppq_b200 observers on the GPU.
     minmax (per tensor / per channel): scales and offsets must equal the reference CPU pipeline's (tests/golden/observers.npz).

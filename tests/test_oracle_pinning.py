@@ -217,3 +217,25 @@ def test_quantile_indices(oracle):
     out = oracle.quantile_t(x, 0.9999)
     assert out[0] == 9999.0 and out[1] == 1.0
     assert np.array_equal(oracle.quantile_t(np.float32([3.0]), 0.9999), np.float32([3.0, 3.0]))
+
+
+def test_fp8_and_histogram_vs_reference_cuda_kernels(oracle):
+    """Vectors produced ON THE B200 BY THE REFERENCE'S OWN CUDA KERNELS (oracle/_ref/PPQ_Cuda_Impls_ref.so; written by
+    tests/test_gpu_vs_reference_cuda.py, committed under tests/golden/ref_cuda_*.npz): this pins the C restatement of the paths that have
+    no CPU implementation upstream -- QuantizeTensor_FT (all tie / subnormal / saturation / special-value cases, two rounding modes,
+    four formats) and Histogram_T."""
+    import re
+    g = load_golden('ref_cuda_fp8.npz')
+    x = g['x']
+    n = 0
+    for key in g.files:
+        m = re.fullmatch(r'y_E(\d)M(\d)_c(\d+)_s([\d.]+)_o([\d.]+)_m(\d)', key)
+        if not m: continue
+        E, M, c, s, o, mode = int(m[1]), int(m[2]), float(m[3]), float(m[4]), float(m[5]), int(m[6])
+        y = oracle.float_quant_t(x, s, o, E, M, -c, c, mode)
+        assert np.array_equal(y.view(np.uint32), g[key].view(np.uint32)), key
+        n += 1
+    assert n >= 8
+    h = load_golden('ref_cuda_hist.npz')
+    got = oracle.histogram_t(h['x'], h['hist_scale'], 4096, True)
+    assert np.array_equal(got, h['hist'])
