@@ -254,6 +254,13 @@ class RuntimeCalibrationPass:
         if calib_steps is not None: self._calib_steps = calib_steps
         assert calib_steps >= 8, 'Insufficient Calibration Detected (at least 8 calibration steps).'
         assert calib_steps <= 512, 'Calibration steps is too large, ppq can quantize your network within 8-512 calibration steps.'
+        if self._override:                                   # calibration.py:147-155: re-calibrate already activated activations
+            from .core import set_state, state_is
+            for _, operation in graph.quantable_operations():
+                for _, config, is_param in operation.input_configs():
+                    if not is_param and state_is(config, 'ACTIVATED'): set_state(config, 'INITIAL')
+                for _, config in operation.output_configs():
+                    if state_is(config, 'ACTIVATED'): set_state(config, 'INITIAL')
         hooks = {}
         for op_name, operation in graph.quantable_operations():
             for _, config, is_param in operation.input_configs():

@@ -284,6 +284,38 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
     return cal
 
 
+@torch.no_grad()
+def graphwise_error_analyse(executor: TorchExecutor, batches, to_device=None) -> Dict[str, float]:
+    """The evaluation loop where fake-quant throughput shows up in user wall-clock (ppq/quantization/analyse/graphwise.py:64-183): run every batch
+    through the network twice -- all configs dequantised (fp32) and all configs active -- and report, per quantable operation, the SNR
+    mean((q - f)^2) / mean(f^2) per sample, averaged (torch_snr_error, ppq/quantization/measure/norm.py:52-93).  Every activation goes through
+    QuantizeTensor_LT and every weight through the multi-tensor QuantizeTensor_LC on each quantised forward."""
+    from .core import set_state
+    cfgs = executor.observed_configs_all() + [op.weight_cfg for _, op in executor.quantable_operations() if op.weight_cfg is not None]
+    saved = [c.state for c in cfgs]
+    names = [n for n, op in executor.quantable_operations()]
+    acc = {n: [0.0, 0] for n in names}
+
+    class Tap:
+        def __init__(self, name, store): self.name, self.store = name, store
+        def pre_forward_hook(self, **kw): pass
+        def post_forward_hook(self, outputs, quant_outputs, quant_configs): self.store[self.name] = quant_outputs[0]
+
+    for x in batches:
+        if to_device is not None: x = to_device(x)
+        fp, qt = {}, {}
+        for c in cfgs: c.state = type(c.state)['FP32'] if getattr(c.state, 'name', '') in ('ACTIVATED', 'PASSIVE') else c.state
+        executor.forward(x, hooks={n: Tap(n, fp) for n in names})
+        for c, st in zip(cfgs, saved): c.state = st
+        executor.forward(x, hooks={n: Tap(n, qt) for n in names})
+        for n in names:
+            f, q = fp[n].flatten(1), qt[n].flatten(1)
+            snr = (torch.pow(q - f, 2).sum(dim=-1) / (torch.pow(f, 2).sum(dim=-1) + 1e-7)).mean()
+            acc[n][0] += float(snr); acc[n][1] += 1
+    for c, st in zip(cfgs, saved): c.state = st
+    return {n: v[0] / max(v[1], 1) for n, v in acc.items()}
+
+
 def e2e_calibration_benchmark(batch: int, steps: int, warmup: int, device, world: int = 1, seed: int = 0, graphs: bool = False):
     """bench.py's `e2e`: ResNet-50 (random init, BN folded) calibrated end to end through the public API -- images in pinned host
     memory, H2D copy of every batch inside the timed region (both phases), torch forward with per-forward weight fake-quant,

@@ -182,3 +182,43 @@ def PPQuantFunction_toInt(tensor: torch.Tensor, config: TensorQuantizationConfig
             return PPQLinearQuant_toInt(tensor, config)
     raise ValueError('Unexpected Quantization Property Found in PPQuantFunction_toInt. '
                      'Do not konw how to quantize your config yet.')
+
+
+class CuLSQ_LT(Function):
+    """ppq/quantization/algorithm/training.py:17-52: learned-step-size quantisation, per tensor.  Forward = the fake-quant kernel,
+    backward = QuantizeTensor_LT_B (grad_x with the clip mask, grad_scale reduced on the device)."""
+    @staticmethod
+    def forward(ctx, tensor, scales, offsets, quant_min: int, quant_max: int, rounding) -> torch.Tensor:
+        _require_cuda(tensor)
+        r = _rounding_value(rounding)
+        quantized = CUDA.LinearQuantize_T(tensor=tensor, scales=scales, offsets=offsets, minimum=quant_min, maximum=quant_max, rounding=r)
+        ctx.save_for_backward(tensor, scales, offsets)
+        ctx._quant_params = [quant_min, quant_max, r]
+        return quantized
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        tensor, scales, offsets = ctx.saved_tensors
+        quant_min, quant_max, rounding = ctx._quant_params
+        dx, ds = CUDA.LinearQuantize_T_B(tensor, scales, offsets, dy.contiguous(), quant_min, quant_max, rounding)
+        return dx, ds, None, None, None, None
+
+
+class CuLSQ_LC(Function):
+    """training.py:55-90: per-channel variant (QuantizeTensor_LC_B)."""
+    @staticmethod
+    def forward(ctx, tensor, scales, offsets, channel_axis: int, quant_min: int, quant_max: int, rounding) -> torch.Tensor:
+        _require_cuda(tensor)
+        r = _rounding_value(rounding)
+        quantized = CUDA.LinearQuantize_C(tensor=tensor, scales=scales, offsets=offsets, channel_axis=channel_axis,
+                                          minimum=quant_min, maximum=quant_max, rounding=r)
+        ctx.save_for_backward(tensor, scales, offsets)
+        ctx._quant_params = [quant_min, quant_max, channel_axis, r]
+        return quantized
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        tensor, scales, offsets = ctx.saved_tensors
+        quant_min, quant_max, channel_axis, rounding = ctx._quant_params
+        dx, ds = CUDA.LinearQuantize_C_B(tensor, scales, offsets, dy.contiguous(), quant_min, quant_max, channel_axis, rounding)
+        return dx, ds, None, None, None, None, None

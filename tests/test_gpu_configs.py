@@ -158,6 +158,11 @@ def test_executor_calibration_paths_agree(ext):
     cal = calibrate_arena(ex2, data, method='kl')
     assert torch.equal(cal.scale, s1)
     assert all(c.state == QuantizationStates.ACTIVATED for c in ex2.observed_configs_all())
+    # evaluation loop (graphwise error analysis): per-op SNR of the quantised network vs fp32, all below the reference's 0.1 bar
+    from ppq_b200.executor import graphwise_error_analyse
+    report = graphwise_error_analyse(ex2, data[:2])
+    assert len(report) == len(ex2.quantable_operations()) and all(0 <= v < 0.1 for v in report.values()), max(report.values())
+    assert all(c.state == QuantizationStates.ACTIVATED for c in ex2.observed_configs_all())       # states restored
     # CUDA-graph replay of the whole forward (network + weight fake-quant + collectors): identical statistics
     ex3 = build()
     cal3 = calibrate_arena(ex3, data, method='kl', graphs=True)

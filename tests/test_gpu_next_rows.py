@@ -197,3 +197,24 @@ def test_tensor_clip_and_rounding_loss(ext, ref):
             assert close(loss_t, ref.RoundingLoss_LT(v, s, o, -128, 127, 0)) and close(loss_c, ref.RoundingLoss_LC(v, sc, oc, -128, 127, c, 0))
             assert same_bits(gt, ref.RoundingLoss_LT_B(v, dyy, s, o, -128, 127, 0)), shape
             assert same_bits(gc, ref.RoundingLoss_LC_B(v, dyy, sc, oc, -128, 127, c, 0)), shape
+
+
+def test_culsq_autograd_functions(ext):
+    """CuLSQ_LT / _LC (algorithm/training.py:17-90) through autograd: grad wrt the tensor is the clip-masked STE, grad wrt the scale is the LSQ term."""
+    from ppq_b200.core import RoundingPolicy
+    from ppq_b200.qfunction import CuLSQ_LC, CuLSQ_LT
+    g = torch.Generator(device='cuda').manual_seed(9)
+    x = (torch.rand(6, 8, 16, 16, device='cuda', generator=g) * 40).requires_grad_()
+    s = torch.tensor([0.11], device='cuda', requires_grad=True); o = torch.tensor([3.0], device='cuda')
+    y = CuLSQ_LT.apply(x, s, o, 0, 255, RoundingPolicy.ROUND_HALF_EVEN)
+    w = torch.rand(y.shape, device='cuda', generator=g)
+    (y * w).sum().backward()
+    dx, ds = lsq_reference(x.detach(), w, s.detach(), o, 0, 255)
+    assert torch.equal(x.grad, dx) and close(s.grad, (ds.double().sum() / sqrt(x.numel() * 255)).float().view(1), rtol=1e-3)
+    x2 = x.detach().clone().requires_grad_()
+    sc = (torch.rand(8, device='cuda', generator=g) * 0.2 + 0.05).requires_grad_(); oc = torch.zeros(8, device='cuda')
+    y = CuLSQ_LC.apply(x2, sc, oc, 1, -128, 127, RoundingPolicy.ROUND_HALF_EVEN)
+    (y * w).sum().backward()
+    dx, ds = lsq_reference(x2.detach(), w, sc.detach(), oc, -128, 127, 1)
+    assert torch.equal(x2.grad, dx)
+    assert close(sc.grad, (ds.double().transpose(0, 1).flatten(1).sum(dim=-1) / sqrt(x2.numel() * 127)).float(), rtol=1e-3, atol=1e-5)
