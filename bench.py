@@ -372,14 +372,15 @@ def cpu_steps(batch, steps, seed=0):
 def cpu_baseline(args, sample_steps):
     """Bounded sample sized from a 1-image probe so that the timed part is about 10-20 s of CPU work on this host."""
     import oracle as ora
-    probe = cpu_steps(1, 1)
-    b = max(1, min(args.batch, int(12.0 / max(probe, 1e-3))))
+    cpu_steps(1, 1)                                                     # warm-up (allocator, thread pool), discarded
+    probe = cpu_steps(2, 1) / 2.0                                       # seconds per image
+    b = max(2, min(args.batch, int(12.0 / max(probe, 1e-3))))
     steps = max(1, min(4, int(12.0 / max(probe * b, 1e-3))))
     secs = cpu_steps(b, steps)
     return {'value': round(steps * b / secs, 2), 'unit': UNIT, 'cores': ora.host_threads(), 'kind': 'port',
             'sample': f'{steps} calibration batch(es) of {b} image(s) (the GPU arm: {args.steps} x {args.batch}): per-forward weight fake-quant, min/max + histc over '
                       f'the 106 activation tensors, KL search; torch CPU ops (oracle/ restatement of the reference USING_CUDA_KERNEL=False path) on '
-                      f'{ora.host_threads()} threads (host reports {os.cpu_count()} CPUs); {secs:.1f} s (1-image probe {probe:.2f} s)'}
+                      f'{ora.host_threads()} threads (host reports {os.cpu_count()} CPUs); {secs:.1f} s (probe {probe:.2f} s/image)'}
 
 
 def run_reference(args, rank, world):

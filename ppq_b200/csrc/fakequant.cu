@@ -256,7 +256,7 @@ static int launch_tensor(const float *x, OutT *y, int64_t n, const float *scale,
                          typename Op::Params p, cudaStream_t st) {
     if (n <= 0 || !x || !y || !scale || !offset) return (int)cudaErrorInvalidValue;
     const bool vec = aligned16(x) && out_aligned<OutT>(y);
-    if (vec && n >= (int64_t)1 << 25) {
+    if (vec && Op::kLight && sizeof(OutT) == 4 && n >= (int64_t)1 << 25) {
         // >= 32 M elements: 8 loads in flight per thread (4 KB contiguous per warp) measured 92 % vs 89 % of HBM peak; below that the
         // coarser work granularity costs more in the tail than the extra memory-level parallelism gains (82 % vs 71 % at 8 M elements)
         ew_tensor_kernel<Op, OutT, true, 8><<<grid_for((n + 3) / 4, kThreads, 8, 16), kThreads, 0, st>>>(x, y, n, scale, offset, p);

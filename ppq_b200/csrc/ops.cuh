@@ -19,6 +19,7 @@ __device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.
 template <int MODE>
 struct LinearOp {
     struct Params { int lo, hi, mode; };
+    static constexpr bool kLight = (MODE == RND_HALF_EVEN);          // few registers per element: the 8-deep load variant pays off
     struct Plan {
         int lo, hi, mode;
         __device__ __forceinline__ explicit Plan(const Params &p) : lo(p.lo), hi(p.hi), mode(p.mode) {}
@@ -52,6 +53,7 @@ struct LinearOp {
 template <int MODE, bool FAST = false>
 struct FloatOp {
     struct Params { int E, M, mode; float cmin, cmax; };
+    static constexpr bool kLight = FAST;
     struct Plan {
         float hi, lo, cmin, cmax, min_sub, inv_min_sub, sub_magic;
         uint32_t sub_thresh_bits, half_minus1, keep_mask; int M, mode;
