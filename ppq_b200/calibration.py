@@ -99,22 +99,26 @@ class ArenaCalibrator:
         self.hist.zero_()
         self.phase = 1
 
-    def _descs(self, tensors: Sequence[torch.Tensor]):
-        key = tuple((t.data_ptr(), t.numel()) for t in tensors)
+    def _descs(self, tensors: Sequence[torch.Tensor], slots: Optional[Sequence[int]] = None):
+        if slots is None:
+            assert len(tensors) == self.T, f'expected {self.T} tensors per forward, got {len(tensors)}'
+            slots = range(self.T)
+        key = tuple((t.data_ptr(), t.numel(), i) for t, i in zip(tensors, slots))
         hit = self._desc_cache.get(key)
         if hit is None:
-            assert len(tensors) == self.T, f'expected {self.T} tensors per forward, got {len(tensors)}'
             for t in tensors:
                 if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                     raise RuntimeError('ArenaCalibrator needs contiguous fp32 CUDA tensors')
-            host = torch.tensor([[p, n, i] for i, (p, n) in enumerate(key)], dtype=torch.int64).pin_memory()
-            hit = (host.to(self.device, non_blocking=True), max(n for _, n in key))
+            host = torch.tensor([[p, n, i] for (p, n, i) in key], dtype=torch.int64).pin_memory()
+            hit = (host.to(self.device, non_blocking=True), max(n for _, n, _ in key))
             if len(self._desc_cache) < 64: self._desc_cache[key] = hit
         return hit
 
     @torch.no_grad()
-    def observe(self, tensors: Sequence[torch.Tensor]):
-        descs, max_n = self._descs(tensors)
+    def observe(self, tensors: Sequence[torch.Tensor], slots: Optional[Sequence[int]] = None):
+        """One multi-tensor launch over `tensors`; tensor j accumulates into arena slot slots[j] (default: j)."""
+        if len(tensors) == 0: return
+        descs, max_n = self._descs(tensors, slots)
         if self.phase == 1:
             self.ext.Multi_MinMax_T(descs, max_n, self.minmax)
         else:

@@ -22,18 +22,27 @@ namespace ppqb {
 template <class Op, class OutT> struct Emit;
 template <class Op> struct Emit<Op, float> {
     static __device__ __forceinline__ float one(const Op &op, float x) { return op.apply(x); }
+    static __device__ __forceinline__ void store4(float *y, int64_t vi, float a, float b, float c, float d) {
+        reinterpret_cast<float4 *>(y)[vi] = make_float4(a, b, c, d);
+    }
     static __device__ __forceinline__ void vec(const Op &op, const float4 &v, float *y, int64_t vi) {
         reinterpret_cast<float4 *>(y)[vi] = op.apply4(v);
     }
 };
 template <class Op> struct Emit<Op, int32_t> {
     static __device__ __forceinline__ int32_t one(const Op &op, float x) { return op.quant(x); }
+    static __device__ __forceinline__ void store4(int32_t *y, int64_t vi, int32_t a, int32_t b, int32_t c, int32_t d) {
+        reinterpret_cast<int4 *>(y)[vi] = make_int4(a, b, c, d);
+    }
     static __device__ __forceinline__ void vec(const Op &op, const float4 &v, int32_t *y, int64_t vi) {
         reinterpret_cast<int4 *>(y)[vi] = op.quant4(v);
     }
 };
 template <class Op> struct Emit<Op, int8_t> {       // also used for uint8 (same low byte)
     static __device__ __forceinline__ int8_t one(const Op &op, float x) { return (int8_t)op.quant(x); }
+    static __device__ __forceinline__ void store4(int8_t *y, int64_t vi, int8_t a, int8_t b, int8_t c, int8_t d) {
+        reinterpret_cast<uint32_t *>(y)[vi] = ((uint32_t)(uint8_t)a) | ((uint32_t)(uint8_t)b << 8) | ((uint32_t)(uint8_t)c << 16) | ((uint32_t)(uint8_t)d << 24);
+    }
     static __device__ __forceinline__ void vec(const Op &op, const float4 &v, int8_t *y, int64_t vi) {
         const int4 q = op.quant4(v);
         reinterpret_cast<uint32_t *>(y)[vi] = ((uint32_t)q.x & 0xFFu) | (((uint32_t)q.y & 0xFFu) << 8) |
@@ -161,13 +170,30 @@ __device__ __forceinline__ void channel_generic_body(const float *__restrict__ x
                                                      const float *__restrict__ scale, const float *__restrict__ offset,
                                                      const typename Op::Plan &plan, int64_t first, int64_t stride) {
     const int64_t groups = (n + 3) >> 2;
+    // 16-byte aligned bases: one 128-bit load / store per group even though the four elements may belong to different channels
+    // (four scalar no-allocate loads of the same 128-byte line would fetch it from L2 four times)
+    const bool al = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(y) & (4 * sizeof(OutT) - 1)) == 0);
     for (int64_t g = first; g < groups; g += stride) {
         const int64_t e0 = g << 2;
         int64_t row = (int64_t)div_epc.quot((uint64_t)e0);
         int64_t col = e0 - row * epc;
         int c = (int)(row - (int64_t)div_C.quot((uint64_t)row) * C);
         const int cnt = (int)((n - e0) < 4 ? (n - e0) : 4);
-        if (col + cnt <= epc) {                                      // all in one row: one operator for the group
+        if (al && cnt == 4) {
+            const float4 v = ld_stream4(reinterpret_cast<const float4 *>(x) + g);
+            const float in[4] = {v.x, v.y, v.z, v.w};
+            OutT out[4];
+            Op op(plan, __ldg(scale + c), __ldg(offset + c));
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                out[j] = Emit<Op, OutT>::one(op, in[j]);
+                if (++col == epc) {                                  // next element starts a new channel row
+                    col = 0; if (++c == C) c = 0;
+                    if (j < 3) op.rebind(__ldg(scale + c), __ldg(offset + c));
+                }
+            }
+            Emit<Op, OutT>::store4(y, g, out[0], out[1], out[2], out[3]);
+        } else if (col + cnt <= epc) {                               // all in one row: one operator for the group
             const Op op(plan, __ldg(scale + c), __ldg(offset + c));
             for (int j = 0; j < cnt; j++) y[e0 + j] = Emit<Op, OutT>::one(op, ld_stream1(x + e0 + j));
         } else {

@@ -29,6 +29,7 @@ struct LinearOp {
         d.init(s);
         o = offset_to_int(off);
     }
+    __device__ __forceinline__ void rebind(float s, float off) { d.init(s); o = offset_to_int(off); }     // same plan, next channel
     __device__ __forceinline__ int finish(float t) const {
         int q;
         if constexpr (MODE >= 0) q = round2int<MODE>(t); else q = round2int_dyn(t, mode);
@@ -74,6 +75,7 @@ struct FloatOp {
     };
     const Plan &pl; ExactDiv d; float off;
     __device__ __forceinline__ FloatOp(const Plan &p, float s, float o) : pl(p), off(o) { d.init(s); }
+    __device__ __forceinline__ void rebind(float s, float o) { d.init(s); off = o; }
     static constexpr float kDivLimit = 1.15e18f;                                        // ~2^60: beyond this use div.rn
     // u = x / s already computed exactly; returns the value on the FP(E,M) grid
     __device__ __forceinline__ float grid(float u) const {

@@ -177,13 +177,15 @@ class TorchExecutor:
         return qout if qout is not output else None
 
     def _emit(self, tensor: torch.Tensor):
-        if self._sink is not None: self._sink(len(self._collected), tensor)    # immediate: the k-th observed tensor of this forward
-        self._collected.append(tensor if self._sink is None else None)
+        # sink(k, tensor) observes the k-th observed tensor of this forward immediately; unless it returns False the tensor is consumed
+        consumed = self._sink is not None and self._sink(len(self._collected), tensor) is not False
+        self._collected.append(None if consumed else tensor)
 
     @torch.no_grad()
     def forward(self, inputs: torch.Tensor, hooks: Optional[dict] = None, collect: bool = False, sink=None):
         """torch.py:365-410.  `collect=True` returns (output, observed fp32 tensors) for a deferred multi-tensor launch -- only
-        valid when the network does not overwrite them in place; `sink(k, tensor)` observes the k-th tensor immediately."""
+        valid for tensors the network does not overwrite in place; `sink(k, tensor)` observes the k-th tensor immediately (a sink that
+        returns False leaves the tensor in the collected list instead)."""
         self._hooks, self._collect, self._sink = hooks, collect or sink is not None, sink
         self._begin()
         out = self.model(inputs)
@@ -232,12 +234,14 @@ class TorchExecutor:
 
 # ------------------------------------------------------------------------------------------------------------------ calibration drivers
 @torch.no_grad()
-def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=None, to_device=None, deferred: bool = False,
+def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=None, to_device=None, deferred='auto',
                     graphs: bool = False):
     """Two-phase calibration of every observed activation through one ArenaCalibrator (statistics arena, one all-reduce per
     phase, on-device scale search).  `batches` is this rank's share of the calibration set (sample-sharded by the caller).
-    deferred=False observes each tensor as the forward produces it (torchvision networks add residuals in place);
-    deferred=True keeps the tensors alive and issues ONE multi-tensor launch per forward;
+    deferred=False observes each tensor as the forward produces it (one launch per tensor);
+    deferred=True keeps all tensors alive and issues ONE multi-tensor launch per forward (only valid when nothing is overwritten in place);
+    deferred='auto' (default) finds out during the first forward which observed tensors the network later overwrites in place
+    (torchvision adds residuals with `out += identity`), observes those immediately and everything else in one multi-tensor launch;
     graphs=True captures one forward per phase -- network kernels, per-forward weight fake-quant and the collectors -- into a CUDA
     graph and replays it for every batch (fixed batch shape).  Measured on B200 (ResNet-50, 8 x 32 images): capture + instantiate
     costs more than it saves at 8-16 batches per phase (1330 vs 3124 imgs/s end to end), so it is off by default; it pays off for long
@@ -248,6 +252,7 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
     dev = next(executor.model.parameters()).device
     cal = ArenaCalibrator(len(cfgs), dev, method=method, group=group)
     static_in = None
+    mutated = None                                                        # slots whose tensors are overwritten later in the forward
     while True:
         graph = None
         for x in batches:
@@ -272,10 +277,28 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
                 graph.replay()
                 continue
             if to_device is not None: x = to_device(x)
-            if deferred:
+            if deferred is True:
                 _, tensors = executor.forward(x, collect=True)
                 cal.observe([t if t.is_contiguous() else t.contiguous() for t in tensors])
                 del tensors
+            elif deferred == 'auto':
+                if mutated is None:                                       # probe forward: observe immediately, remember versions
+                    seen = []
+
+                    def probe(k, t):
+                        cal.observe_one(k, t); seen.append((t, t._version))
+                    executor.forward(x, sink=probe)
+                    mutated = {k for k, (t, v) in enumerate(seen) if t._version != v or not t.is_contiguous()}
+                    del seen
+                else:
+                    def sink(k, t):
+                        if k in mutated:
+                            cal.observe_one(k, t); return True
+                        return False
+                    _, tensors = executor.forward(x, collect=True, sink=sink)
+                    rest = [(k, t) for k, t in enumerate(tensors) if t is not None]
+                    cal.observe([t for _, t in rest], [k for k, _ in rest])
+                    del tensors, rest
             else:
                 executor.forward(x, sink=cal.observe_one)
         if cal.end_phase(): break

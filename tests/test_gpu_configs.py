@@ -155,8 +155,11 @@ def test_executor_calibration_paths_agree(ext):
     RuntimeCalibrationPass(method='kl').optimize(graph=ex1, dataloader=data, executor=ex1, calib_steps=8)
     s1 = torch.stack([c.scale for c in ex1.observed_configs_all()])
     ex2 = build()
-    cal = calibrate_arena(ex2, data, method='kl')
+    cal = calibrate_arena(ex2, data, method='kl', deferred=False)
     assert torch.equal(cal.scale, s1)
+    ex4 = build()
+    cal4 = calibrate_arena(ex4, data, method='kl')                         # deferred='auto': multi-tensor launch for everything not overwritten in place
+    assert torch.equal(cal4.minmax, cal.minmax) and torch.equal(cal4.hist, cal.hist) and torch.equal(cal4.scale, s1)
     assert all(c.state == QuantizationStates.ACTIVATED for c in ex2.observed_configs_all())
     # evaluation loop (graphwise error analysis): per-op SNR of the quantised network vs fp32, all below the reference's 0.1 bar
     from ppq_b200.executor import graphwise_error_analyse
