@@ -108,6 +108,18 @@ struct ExactDiv {
     }
 };
 
+// Four quotients by four different divisors (channel-last layouts: neighbouring elements belong to different channels), one range test.
+__device__ __forceinline__ float4 exact_div4x(const ExactDiv &a, const ExactDiv &b, const ExactDiv &c, const ExactDiv &d,
+                                              const float4 &x, float limit = 2147483648.f) {
+    float4 q = make_float4(a.fast(x.x), b.fast(x.y), c.fast(x.z), d.fast(x.w));
+    const uint32_t m = max(max(__float_as_uint(q.x) & 0x7FFFFFFFu, __float_as_uint(q.y) & 0x7FFFFFFFu),
+                           max(__float_as_uint(q.z) & 0x7FFFFFFFu, __float_as_uint(q.w) & 0x7FFFFFFFu));
+    if (m >= __float_as_uint(limit)) {
+        q.x = ieee_div_slow(x.x, a.s); q.y = ieee_div_slow(x.y, b.s); q.z = ieee_div_slow(x.z, c.s); q.w = ieee_div_slow(x.w, d.s);
+    }
+    return q;
+}
+
 // ---- streaming global memory access -----------------------------------------------------------------------
 // Inputs are read exactly once: bypass L1 allocation (ld.global.nc.L1::no_allocate).  Outputs are written with
 // the default policy so that they stay in the 126 MB L2 for the consumer kernel (the next operator of the graph).

@@ -28,6 +28,9 @@ template <class Op> struct Emit<Op, float> {
     static __device__ __forceinline__ void vec(const Op &op, const float4 &v, float *y, int64_t vi) {
         reinterpret_cast<float4 *>(y)[vi] = op.apply4(v);
     }
+    static __device__ __forceinline__ void vecx(const Op (&ops)[4], const float4 &v, float *y, int64_t vi) {
+        reinterpret_cast<float4 *>(y)[vi] = Op::apply4x(ops, v);
+    }
 };
 template <class Op> struct Emit<Op, int32_t> {
     static __device__ __forceinline__ int32_t one(const Op &op, float x) { return op.quant(x); }
@@ -37,6 +40,9 @@ template <class Op> struct Emit<Op, int32_t> {
     static __device__ __forceinline__ void vec(const Op &op, const float4 &v, int32_t *y, int64_t vi) {
         reinterpret_cast<int4 *>(y)[vi] = op.quant4(v);
     }
+    static __device__ __forceinline__ void vecx(const Op (&ops)[4], const float4 &v, int32_t *y, int64_t vi) {
+        reinterpret_cast<int4 *>(y)[vi] = Op::quant4x(ops, v);
+    }
 };
 template <class Op> struct Emit<Op, int8_t> {       // also used for uint8 (same low byte)
     static __device__ __forceinline__ int8_t one(const Op &op, float x) { return (int8_t)op.quant(x); }
@@ -45,6 +51,11 @@ template <class Op> struct Emit<Op, int8_t> {       // also used for uint8 (same
     }
     static __device__ __forceinline__ void vec(const Op &op, const float4 &v, int8_t *y, int64_t vi) {
         const int4 q = op.quant4(v);
+        reinterpret_cast<uint32_t *>(y)[vi] = ((uint32_t)q.x & 0xFFu) | (((uint32_t)q.y & 0xFFu) << 8) |
+                                              (((uint32_t)q.z & 0xFFu) << 16) | (((uint32_t)q.w & 0xFFu) << 24);
+    }
+    static __device__ __forceinline__ void vecx(const Op (&ops)[4], const float4 &v, int8_t *y, int64_t vi) {
+        const int4 q = Op::quant4x(ops, v);
         reinterpret_cast<uint32_t *>(y)[vi] = ((uint32_t)q.x & 0xFFu) | (((uint32_t)q.y & 0xFFu) << 8) |
                                               (((uint32_t)q.z & 0xFFu) << 16) | (((uint32_t)q.w & 0xFFu) << 24);
     }
@@ -160,6 +171,29 @@ ew_channel_vec_kernel(const float *__restrict__ x, OutT *__restrict__ y, uint32_
                       const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
     const typename Op::Plan plan(p);
     channel_vec_body<Op, OutT>(x, y, n4, C, div_epc4, div_C, scale, offset, plan, blockIdx.x * kThreads + threadIdx.x, gridDim.x * kThreads);
+}
+
+// ---- per-channel, channel-last (epc == 1, C % 4 == 0): x is [rows, C], element (r, c) belongs to channel c ---------------------
+// The grid-stride is rounded down to a multiple of C/4, so every thread keeps meeting the same four channels: their operators
+// (exact reciprocals, integer offsets) are built once per thread and the loop body costs what the per-tensor kernel costs.
+template <class Op, class OutT>
+__global__ void __launch_bounds__(kThreads)
+ew_channel_last_kernel(const float *__restrict__ x, OutT *__restrict__ y, int64_t n4, uint32_t C4, uint32_t active,
+                       const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
+    const typename Op::Plan plan(p);
+    const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;
+    if (tid >= active) return;
+    const uint32_t c = (tid % C4) * 4;
+    const Op ops[4] = {Op(plan, __ldg(scale + c), __ldg(offset + c)), Op(plan, __ldg(scale + c + 1), __ldg(offset + c + 1)),
+                       Op(plan, __ldg(scale + c + 2), __ldg(offset + c + 2)), Op(plan, __ldg(scale + c + 3), __ldg(offset + c + 3))};
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (int64_t base = tid; base < n4; base += (int64_t)active * kUnroll) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) if (base + (int64_t)j * active < n4) v[j] = ld_stream4(x4 + base + (int64_t)j * active);
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) if (base + (int64_t)j * active < n4) Emit<Op, OutT>::vecx(ops, v[j], y, base + (int64_t)j * active);
+    }
 }
 
 // ---- per-channel, generic: any epc (1, 9, 27, ...), any alignment ---------------------------------------------------------
@@ -311,6 +345,15 @@ static int launch_channel(const float *x, OutT *y, int64_t n, int64_t epc, int C
             const int grid = grid_for(n4, kThreads, kUnroll, 16);
             ew_channel_vec_kernel<Op, OutT><<<grid, kThreads, 0, st>>>(x, y, (uint32_t)n4, C, FastDiv32((uint32_t)(epc / 4)), FastDiv32((uint32_t)C),
                                                                           scale, offset, p);
+            return (int)cudaGetLastError();
+        }
+    }
+    if (epc == 1 && C % 4 == 0 && aligned16(x) && out_aligned<OutT>(y)) {
+        const int64_t n4 = n / 4, C4 = C / 4;
+        const int grid = grid_for(n4, kThreads, kUnroll, 8);
+        const int64_t threads = (int64_t)grid * kThreads;
+        if (threads >= C4) {
+            ew_channel_last_kernel<Op, OutT><<<grid, kThreads, 0, st>>>(x, y, n4, (uint32_t)C4, (uint32_t)(threads / C4 * C4), scale, offset, p);
             return (int)cudaGetLastError();
         }
     }

@@ -46,6 +46,15 @@ struct LinearOp {
         const int4 q = quant4(v);
         return make_float4(dequant(q.x), dequant(q.y), dequant(q.z), dequant(q.w));
     }
+    // lane j of the vector belongs to operator o[j] (channel-last layouts)
+    static __device__ __forceinline__ int4 quant4x(const LinearOp (&o)[4], const float4 &v) {
+        const float4 t = exact_div4x(o[0].d, o[1].d, o[2].d, o[3].d, v);
+        return make_int4(o[0].finish(t.x), o[1].finish(t.y), o[2].finish(t.z), o[3].finish(t.w));
+    }
+    static __device__ __forceinline__ float4 apply4x(const LinearOp (&o)[4], const float4 &v) {
+        const int4 q = quant4x(o, v);
+        return make_float4(o[0].dequant(q.x), o[1].dequant(q.y), o[2].dequant(q.z), o[3].dequant(q.w));
+    }
 };
 
 // FAST (HALF_EVEN only, chosen on the host by float_fast_path_ok): the branch-free path, valid when both saturation bounds are
@@ -120,6 +129,10 @@ struct FloatOp {
     __device__ __forceinline__ float4 apply4(const float4 &v) const {
         const float4 u = d.div4(v, kDivLimit);
         return make_float4(dequant(grid(u.x)), dequant(grid(u.y)), dequant(grid(u.z)), dequant(grid(u.w)));
+    }
+    static __device__ __forceinline__ float4 apply4x(const FloatOp (&o)[4], const float4 &v) {
+        const float4 u = exact_div4x(o[0].d, o[1].d, o[2].d, o[3].d, v, kDivLimit);
+        return make_float4(o[0].dequant(o[0].grid(u.x)), o[1].dequant(o[1].grid(u.y)), o[2].dequant(o[2].grid(u.z)), o[3].dequant(o[3].grid(u.w)));
     }
 };
 

@@ -202,6 +202,34 @@ def test_lc_shapes_axes(ext, oracle, shape, axis):
         assert_bits_equal(y, oracle.linear_quant_c(x, s, o, axis, 0, 255, 0), f'LC {shape} axis {axis} sym={sym}')
 
 
+def test_lc_fc_channel_last(ext, oracle):
+    """Channel-last layouts (epc == 1): the dedicated kernel (C % 4 == 0, aligned), its fall-backs (C % 4 != 0, unaligned view, fewer
+    threads than channel groups), every output type, all rounding modes, badly scaled channels (IEEE slow path) and FP8."""
+    r = np.random.RandomState(77)
+    for rows, C in ((197 * 8, 768), (3, 4), (1, 8), (4097, 12), (2, 400000), (1000, 47), (33, 1024)):
+        x = (r.standard_normal((rows, C)) * 6).astype(np.float32)
+        x.reshape(-1)[:: 97] *= 1e6
+        s = (r.rand(C) * 0.1 + 1e-3).astype(np.float32); s[1] = 1e-25; s[C - 2] = 1e25
+        o = r.randint(-5, 5, size=C).astype(np.float32)
+        for mode in ((0, 1, 2, 3, 4, 5, 6, 7) if C == 768 else (0, 4)):
+            y = ext.QuantizeTensor_LC(dev(x), dev(s), dev(o), -128, 127, 1, mode)
+            assert_bits_equal(y, oracle.linear_quant_c(x, s, o, 1, -128, 127, mode), f'LC last [{rows},{C}] mode {mode}')
+        want_q = oracle.linear_quant_c(x, s, o, 1, -128, 127, 0, return_int=True)[1]
+        for bits in (32, 8):
+            q = ext.QuantizeTensor_toInt(dev(x), dev(s), dev(o), -128, 127, 1, 0, bits)
+            assert np.array_equal(q.cpu().numpy().astype(np.int64), want_q.astype(np.int64)), (rows, C, bits)
+        xf = fp_inputs(r, max(rows * C, 32))[:rows * C].reshape(rows, C)
+        sf = np.exp2(r.randint(-4, 4, size=C)).astype(np.float32) * (1 + r.rand(C).astype(np.float32)); sf[0] = 1e-25
+        of = np.zeros(C, np.float32)
+        for mode in (0, 1):
+            y = ext.QuantizeTensor_FC(dev(xf), dev(sf), dev(of), 4, 3, -448.0, 448.0, 1, mode)
+            assert_bits_equal(y, oracle.float_quant_c(xf, sf, of, 1, 4, 3, -448.0, 448.0, mode), f'FC last [{rows},{C}] mode {mode}')
+    base = dev((r.standard_normal(1 + 64 * 256) * 4).astype(np.float32))
+    v = base[1:].view(64, 256)                                          # not 16-byte aligned -> generic kernel
+    s = (r.rand(256) * 0.1 + 1e-3).astype(np.float32); o = np.zeros(256, np.float32)
+    assert_bits_equal(ext.QuantizeTensor_LC(v, dev(s), dev(o), -128, 127, 1, 0), oracle.linear_quant_c(v.cpu().numpy(), s, o, 1, -128, 127, 0), 'unaligned')
+
+
 def test_lc_unaligned_modes_and_special(ext, oracle):
     r = np.random.RandomState(9)
     base = dev((r.standard_normal(3 + 96 * 64) * 4).astype(np.float32))
