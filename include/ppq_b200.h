@@ -75,6 +75,7 @@ typedef struct {
     int32_t      C;        /* channels                        */
     int32_t      pad_;
 } ppq_b200_lc_desc;
+/* count <= 4096 tensors per call, every n <= 2^31 - 1; max_n = the largest n of the table (sizes the grid). */
 PPQ_B200_API int ppq_b200_multi_linear_quant_c(const ppq_b200_lc_desc *descs, int count, int64_t max_n,
                                                int qmin, int qmax, int rounding, void *stream);
 

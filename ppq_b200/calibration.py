@@ -312,9 +312,12 @@ class MultiWeightQuantizer:
             assert s.numel() == C and o.numel() == C
             rows.append([w.data_ptr(), y.data_ptr(), s.data_ptr(), o.data_ptr(), w.numel(), epc, C])
         self.max_n = max(r[4] for r in rows)
-        self.descs = torch.tensor(rows, dtype=torch.int64).to(self.weights[0].device)
+        table = torch.tensor(rows, dtype=torch.int64).to(self.weights[0].device)
+        self.descs = table
+        self._tables = [table[i:i + 4096] for i in range(0, len(rows), 4096)]      # the C ABI takes <= 4096 tensors per launch
 
     @torch.no_grad()
     def __call__(self) -> List[torch.Tensor]:
-        self.ext.Multi_QuantizeTensor_LC(self.descs, self.max_n, self.quant_min, self.quant_max, self.rounding)
+        for table in self._tables:
+            self.ext.Multi_QuantizeTensor_LC(table, self.max_n, self.quant_min, self.quant_max, self.rounding)
         return self.outputs

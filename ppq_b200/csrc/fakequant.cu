@@ -251,54 +251,105 @@ ew_channel_generic_kernel(const float *__restrict__ x, OutT *__restrict__ y, int
 }
 
 // ---- multi-tensor per-channel fake-quant: every Conv/Gemm weight of a network in ONE launch ------------------------------------
-// Work item = (tensor, chunk of kMultiChunk elements); the per-tensor geometry (epc, C, fast-division constants) lives in the
-// descriptor table in device memory.
-constexpr int64_t kMultiChunk = 16384;
+// The tensors are cut into warp segments of 128 vectors (512 elements); the concatenation of all segments is split evenly over the
+// CTAs (the per-tensor segment counts are prefix-summed in shared memory by every CTA, so no host-side table is needed and no CTA
+// visits an empty work item).  Inside a span the 8 warps of a CTA take segments round-robin.  A segment of a tensor with rows of
+// >= 128 vectors lies in one channel row (or straddles one row end): the operator -- exact reciprocal, integer offset -- is built
+// once per 16 elements of a thread.  Shorter rows build one operator per vector; rows that are not a multiple of 4 elements, or
+// unaligned tensors, walk (row, col) element by element but still move 128 bits per access when the bases allow it.
+constexpr int kSegVec = 32 * kUnroll;
+constexpr int kMaxMultiTensors = 4096;              // (count + 1) x 8 bytes of shared memory
 template <class Op>
 __global__ void __launch_bounds__(kThreads)
-multi_channel_kernel(const ppq_b200_lc_desc *__restrict__ descs, int count, int chunks_per_tensor, typename Op::Params p) {
+multi_channel_kernel(const ppq_b200_lc_desc *__restrict__ descs, int count, typename Op::Params p) {
+    extern __shared__ long long seg_prefix[];                          // [count + 1], in segments
+    for (int t = threadIdx.x; t < count; t += kThreads) {
+        const int64_t n = descs[t].n;
+        seg_prefix[t + 1] = n > 0 ? (n + 4 * kSegVec - 1) / (4 * kSegVec) : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long run = 0; seg_prefix[0] = 0;
+        for (int t = 1; t <= count; t++) { run += seg_prefix[t]; seg_prefix[t] = run; }
+    }
+    __syncthreads();
+    const int64_t total = seg_prefix[count];
+    const int64_t span = (total + gridDim.x - 1) / gridDim.x;
+    const int64_t s0 = (int64_t)blockIdx.x * span, s1 = (s0 + span) < total ? (s0 + span) : total;
+    if (s0 >= total) return;
+    int t;
+    { int lo = 0, hi = count - 1; while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (seg_prefix[mid] <= s0) lo = mid; else hi = mid - 1; } t = lo; }
     const typename Op::Plan plan(p);
-    const int64_t items = (int64_t)count * chunks_per_tensor;
-    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        const int t = (int)(item / chunks_per_tensor);
-        const int64_t ck = item - (int64_t)t * chunks_per_tensor;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (; t < count && seg_prefix[t] < s1; t++) {
+        const int64_t first = seg_prefix[t], segs = seg_prefix[t + 1] - first;
+        if (segs == 0) continue;
         const ppq_b200_lc_desc d = descs[t];
-        const int64_t begin = ck * kMultiChunk;
-        if (begin >= d.n) continue;
-        const int64_t len = (d.n - begin) < kMultiChunk ? (d.n - begin) : kMultiChunk;
-        // chunk boundaries are multiples of 4 elements, so group/vector alignment inside a chunk equals that of the tensor
-        const bool vec = (d.epc % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.x) | reinterpret_cast<uintptr_t>(d.y)) & 15u) == 0;
-        if (vec) {
-            const uint32_t v0 = (uint32_t)(begin >> 2), v1 = (uint32_t)((begin + len) >> 2);
-            const FastDiv32 de((uint32_t)(d.epc >> 2)), dc((uint32_t)d.C);
-            const float4 *x4 = reinterpret_cast<const float4 *>(d.x);
-            for (uint32_t i = v0 + threadIdx.x; i < v1; i += kUnroll * kThreads) {
+        const uint32_t a = (uint32_t)(s0 > first ? s0 - first : 0), b = (uint32_t)((s1 - first) < segs ? (s1 - first) : segs);
+        const bool al = ((reinterpret_cast<uintptr_t>(d.x) | reinterpret_cast<uintptr_t>(d.y)) & 15u) == 0;
+        const float4 *x4 = reinterpret_cast<const float4 *>(d.x);
+        if (al && d.epc % 4 == 0) {
+            const uint32_t n4 = (uint32_t)(d.n >> 2), epc4 = (uint32_t)(d.epc >> 2);
+            const FastDiv32 de(epc4), dc((uint32_t)d.C);
+            for (uint32_t sg = a + warp; sg < b; sg += kThreads / 32) {
+                const uint32_t base = sg * kSegVec;
                 float4 v[kUnroll];
 #pragma unroll
-                for (int j = 0; j < kUnroll; j++) if (i + j * kThreads < v1) v[j] = ld_stream4(x4 + i + j * kThreads);
+                for (int j = 0; j < kUnroll; j++) if (base + j * 32 + lane < n4) v[j] = ld_stream4(x4 + base + j * 32 + lane);
+                const uint32_t r0 = de.quot(base);
+                const uint32_t c0 = r0 - dc.quot(r0) * (uint32_t)d.C;
+                if ((r0 + 1) * epc4 >= base + kSegVec) {                 // whole segment inside one channel row (warp-uniform)
+                    const Op op(plan, __ldg(d.scale + c0), __ldg(d.offset + c0));
 #pragma unroll
-                for (int j = 0; j < kUnroll; j++) {
-                    const uint32_t vi = i + j * kThreads;
-                    if (vi < v1) {
-                        const uint32_t row = de.quot(vi);
-                        const uint32_t c = row - dc.quot(row) * (uint32_t)d.C;
-                        const Op op(plan, __ldg(d.scale + c), __ldg(d.offset + c));
-                        Emit<Op, float>::vec(op, v[j], d.y, (int64_t)vi);
+                    for (int j = 0; j < kUnroll; j++) if (base + j * 32 + lane < n4) Emit<Op, float>::vec(op, v[j], d.y, (int64_t)(base + j * 32 + lane));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kUnroll; j++) {
+                        const uint32_t vi = base + j * 32 + lane;
+                        if (vi < n4) {
+                            const uint32_t row = de.quot(vi);
+                            const uint32_t c = row - dc.quot(row) * (uint32_t)d.C;
+                            const Op op(plan, __ldg(d.scale + c), __ldg(d.offset + c));
+                            Emit<Op, float>::vec(op, v[j], d.y, (int64_t)vi);
+                        }
                     }
                 }
             }
         } else {
-            // generic walk restricted to [begin, begin + len)
-            const FastDiv32 de((uint32_t)d.epc), dc((uint32_t)d.C);
-            for (int64_t e0 = begin + 4 * (int64_t)threadIdx.x; e0 < begin + len; e0 += 4 * kThreads) {
-                const uint32_t row = de.quot((uint32_t)e0);
-                int64_t col = e0 - (int64_t)row * d.epc;
-                int c = (int)(row - dc.quot(row) * (uint32_t)d.C);
-                const int cnt = (int)((begin + len - e0) < 4 ? (begin + len - e0) : 4);
-                for (int j = 0; j < cnt; j++) {
-                    const Op op(plan, __ldg(d.scale + c), __ldg(d.offset + c));
-                    d.y[e0 + j] = op.apply(ld_stream1(d.x + e0 + j));
-                    if (++col == d.epc) { col = 0; if (++c == d.C) c = 0; }
+            const uint32_t n = (uint32_t)d.n, epc = (uint32_t)d.epc;
+            const FastDiv32 de(epc), dc((uint32_t)d.C);
+            for (uint32_t sg = a + warp; sg < b; sg += kThreads / 32) {
+                const uint32_t base = sg * kSegVec;
+                float4 v[kUnroll];
+                if (al) {
+#pragma unroll
+                    for (int j = 0; j < kUnroll; j++) if ((uint64_t)(base + j * 32 + lane) * 4 + 4 <= n) v[j] = ld_stream4(x4 + base + j * 32 + lane);
+                }
+#pragma unroll
+                for (int j = 0; j < kUnroll; j++) {
+                    const uint32_t g = base + j * 32 + lane;
+                    const uint64_t e0 = (uint64_t)g * 4;
+                    if (e0 >= n) continue;
+                    const uint32_t row = de.quot((uint32_t)e0);
+                    uint32_t col = (uint32_t)e0 - row * epc;
+                    uint32_t c = row - dc.quot(row) * (uint32_t)d.C;
+                    Op op(plan, __ldg(d.scale + c), __ldg(d.offset + c));
+                    if (al && e0 + 4 <= n) {
+                        const float in[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                        float out[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            out[k] = op.apply(in[k]);
+                            if (++col == epc) { col = 0; if (++c == (uint32_t)d.C) c = 0; if (k < 3) op.rebind(__ldg(d.scale + c), __ldg(d.offset + c)); }
+                        }
+                        reinterpret_cast<float4 *>(d.y)[g] = make_float4(out[0], out[1], out[2], out[3]);
+                    } else {
+                        const int cnt = (int)((n - e0) < 4 ? (n - e0) : 4);
+                        for (int k = 0; k < cnt; k++) {
+                            d.y[e0 + k] = op.apply(ld_stream1(d.x + e0 + k));
+                            if (++col == epc) { col = 0; if (++c == (uint32_t)d.C) c = 0; op.rebind(__ldg(d.scale + c), __ldg(d.offset + c)); }
+                        }
+                    }
                 }
             }
         }
@@ -445,13 +496,13 @@ int ppq_b200_linear_quant_c_toint(const float *x, void *q, int out_bits, int64_t
 }
 
 int ppq_b200_multi_linear_quant_c(const ppq_b200_lc_desc *descs, int count, int64_t max_n, int qmin, int qmax, int rounding, void *stream) {
-    if (count <= 0 || max_n <= 0 || !descs || qmin > qmax) return (int)cudaErrorInvalidValue;
-    const int64_t cpt = (max_n + kMultiChunk - 1) / kMultiChunk;
-    if (cpt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
-    const int64_t items = (int64_t)count * cpt;
-    const int grid = (int)(items < (int64_t)kSMs * 16 ? items : (int64_t)kSMs * 16);
-    if (rounding == RND_HALF_EVEN) multi_channel_kernel<LinearOp<0>><<<grid, kThreads, 0, (cudaStream_t)stream>>>(descs, count, (int)cpt, {qmin, qmax, 0});
-    else multi_channel_kernel<LinearOp<-1>><<<grid, kThreads, 0, (cudaStream_t)stream>>>(descs, count, (int)cpt, {qmin, qmax, rounding});
+    if (count <= 0 || count > kMaxMultiTensors || max_n <= 0 || max_n > 0x7fffffffLL || !descs || qmin > qmax) return (int)cudaErrorInvalidValue;
+    // upper bound of the work (the true total is summed on the device): one CTA per 8 segments of 512 elements, at most 8 CTAs per SM
+    int64_t g = ((int64_t)count * ((max_n + 4 * kSegVec - 1) / (4 * kSegVec)) + 7) / 8;
+    if (g > (int64_t)kSMs * 8) g = (int64_t)kSMs * 8;
+    const size_t smem = (size_t)(count + 1) * sizeof(long long);
+    if (rounding == RND_HALF_EVEN) multi_channel_kernel<LinearOp<0>><<<(int)g, kThreads, smem, (cudaStream_t)stream>>>(descs, count, {qmin, qmax, 0});
+    else multi_channel_kernel<LinearOp<-1>><<<(int)g, kThreads, smem, (cudaStream_t)stream>>>(descs, count, {qmin, qmax, rounding});
     return (int)cudaGetLastError();
 }
 

@@ -246,7 +246,7 @@ def test_multi_tensor_lc_matches_single_launches(ext, oracle):
     """One launch over a table of weights (MobileNetV2-like shapes incl. depth-wise epc = 9, bias-like epc = 1, unaligned views)."""
     from ppq_b200.calibration import MultiWeightQuantizer
     r = np.random.RandomState(77)
-    shapes = [(32, 3, 3, 3), (32, 1, 3, 3), (16, 32, 1, 1), (96, 16, 1, 1), (96, 1, 3, 3), (1280, 320, 1, 1), (1000, 1280), (64,), (7, 5, 3), (512, 512, 3, 3)]
+    shapes = [(32, 3, 3, 3), (32, 1, 3, 3), (16, 32, 1, 1), (96, 16, 1, 1), (96, 1, 3, 3), (1280, 320, 1, 1), (1000, 1280), (64,), (7, 5, 3), (512, 512, 3, 3), (3, 1000), (5, 132), (1, 4), (2, 1, 1, 1)]
     ws = [dev((r.standard_normal(s) * 0.1).astype(np.float32)) for s in shapes]
     ws[4] = dev(np.concatenate([np.zeros(1, np.float32), ws[4].cpu().numpy().reshape(-1)]))[1:].view(96, 1, 3, 3)     # not 16-byte aligned
     scales = [(w.abs().amax(dim=tuple(range(1, w.dim()))) / 127).clamp_min(1e-8) if w.dim() > 1 else (w.abs() / 127).clamp_min(1e-8) for w in ws]
@@ -256,6 +256,10 @@ def test_multi_tensor_lc_matches_single_launches(ext, oracle):
     for w, s, o, y in zip(ws, scales, offsets, outs):
         assert torch.equal(y, ext.QuantizeTensor_LC(w, s, o, -128, 127, 0, 0)), tuple(w.shape)
         assert_bits_equal(y, oracle.linear_quant_c(w.cpu().numpy(), s.cpu().numpy(), o.cpu().numpy(), 0, -128, 127, 0), str(tuple(w.shape)))
+    offsets = [torch.full_like(s, 3.0) for s in scales]
+    outs = MultiWeightQuantizer(ws, scales, offsets, channel_axis=0, quant_min=-8, quant_max=7, rounding=4)()
+    for w, s, o, y in zip(ws, scales, offsets, outs):
+        assert_bits_equal(y, oracle.linear_quant_c(w.cpu().numpy(), s.cpu().numpy(), o.cpu().numpy(), 0, -8, 7, 4), 'int4 mode 4 ' + str(tuple(w.shape)))
 
 
 # ------------------------------------------------------------------------------------------------ FP8 & friends

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel micro-benchmarks (CUDA events, rotating buffers > L2) used to choose variants and to feed ncu.
 
-    python tools/kbench.py [--only hist,lt,lc,ft,minmax] [--reps 20]
+    python tools/kbench.py [--only hist,lt,lc,ft,minmax,multi,quantile,ltshape] [--reps 20]
 """
 import argparse
 import ctypes
@@ -94,6 +94,23 @@ def main():
             secs = timeit(lambda i: ext.QuantizeTensor_LC(vs[i], s, o, -128, 127, axis, 0), args.reps, nbuf)
             gbs = 8 * m / secs / 1e9
             print(f'{"linear_quant_c " + str(shape) + " axis " + str(axis):48s} {secs*1e6:9.1f} us  {gbs:8.1f} GB/s  {gbs/PEAK:6.1%}', flush=True)
+    if 'multi' in only:
+        # every Conv/Linear weight of a network in one launch; copies of the table rotate so that the weights come from HBM, not L2
+        import torchvision
+        from ppq_b200.calibration import MultiWeightQuantizer
+        for name, ctor, copies in (('resnet50', torchvision.models.resnet50, 3), ('mobilenet_v2', torchvision.models.mobilenet_v2, 12)):
+            shapes = [tuple(m.weight.shape) for m in ctor(weights=None).modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))]
+            qs = []
+            for _ in range(copies):
+                ws = [torch.randn(sh, device=dev) * 0.05 for sh in shapes]
+                sc = [w.flatten(1).abs().amax(1) / 127 for w in ws]
+                qs.append(MultiWeightQuantizer(ws, sc, [torch.zeros_like(v) for v in sc], channel_axis=0))
+            m = sum(w.numel() for w in qs[0].weights)
+            secs = timeit(lambda i: qs[i](), args.reps, copies)
+            gbs = 8 * m / secs / 1e9
+            print(f'{"multi_linear_quant_c " + name + f" {len(shapes)} tensors {m/1e6:.1f} M el":48s} {secs*1e6:9.1f} us  {gbs:8.1f} GB/s  {gbs/PEAK:6.1%}', flush=True)
+            one_by_one = timeit(lambda i: [ext.QuantizeTensor_LC(w, s_, o_, -128, 127, 0, 0) for w, s_, o_ in zip(qs[i].weights, qs[i].scales, qs[i].offsets)], max(args.reps // 4, 2), copies)
+            print(f'{"  same, one QuantizeTensor_LC launch per tensor":48s} {one_by_one*1e6:9.1f} us', flush=True)
     if 'ft' in only:
         report('float_quant_t E4M3', timeit(lambda i: ext.QuantizeTensor_FT(xs[i], torch.ones(1, device=dev), zero, 4, 3, -448.0, 448.0, 0), args.reps, nbuf), 8)
         report('float_quant_t E4M3 mode1', timeit(lambda i: ext.QuantizeTensor_FT(xs[i], torch.ones(1, device=dev), zero, 4, 3, -448.0, 448.0, 1), args.reps, nbuf), 8)
