@@ -17,38 +17,43 @@ constexpr int RND_HALF_EVEN = 0, RND_HALF_UP = 1, RND_HALF_DOWN = 2, RND_HALF_TO
 // ---- rounding ---------------------------------------------------------------------------------------
 // All conversions saturate and send NaN to 0 (PTX cvt.*.s32.*), which is what the reference's implicit
 // float->int / double->int conversions compile to.
+// The reference evaluates its "+ .5" modes in double (`floor(value + .5)` promotes the float).  fp64 throughput on this part is a
+// small fraction of fp32, so the same integers are produced in fp32: with t = floor(v), floor(v + .5) = t + [v - t >= .5].  The
+// subtraction may round (tiny negative v: 1 - 1e-30 -> 1), but rounding is monotonic and .5 is representable, so the comparison
+// `>= .5` is decided correctly; a `> .5` comparison would not be, which is why the "half down" form is built on ceil() instead
+// of reusing floor().  Saturation and NaN -> 0 come from the F2I conversion exactly as in the double path (the fraction of a
+// saturated or non-finite v is 0 or NaN, so nothing is added).
+__device__ __forceinline__ int round_half_up(float v)   { return __float2int_rd(v) + (__fsub_rn(v, floorf(v)) >= 0.5f ? 1 : 0); }   // floor(v + .5)
+__device__ __forceinline__ int round_half_down(float v) { return __float2int_ru(v) - (__fsub_rn(ceilf(v), v) >= 0.5f ? 1 : 0); }    // ceil(v - .5)
+
 template <int MODE>
 __device__ __forceinline__ int round2int(float v) {
     if constexpr (MODE == RND_HALF_EVEN) {
         return __float2int_rn(v);                                   // nearbyint -> int  (one F2I)
     } else if constexpr (MODE == RND_HALF_UP) {
-        return __double2int_rd((double)v + 0.5);                    // floor(v + .5) evaluated in fp64
+        return round_half_up(v);
     } else if constexpr (MODE == RND_HALF_DOWN) {
-        return __double2int_ru((double)v - 0.5);                    // ceil(v - .5) in fp64
+        return round_half_down(v);
     } else if constexpr (MODE == RND_HALF_TOWARDS_ZERO) {
-        return v > 0.f ? __double2int_ru((double)v - 0.5) : __double2int_rd((double)v + 0.5);
-    } else if constexpr (MODE == RND_HALF_FAR_FROM_ZERO) {
-        return v > 0.f ? __double2int_rd((double)v + 0.5) : __double2int_ru((double)v - 0.5);
+        return v > 0.f ? round_half_down(v) : round_half_up(v);
     } else if constexpr (MODE == RND_UP) {
         return __float2int_ru(v);
     } else if constexpr (MODE == RND_DOWN) {
         return __float2int_rd(v);
-    } else {
-        return __float2int_rz(roundf(v));                           // round(): half away from zero
+    } else {                                                        // HALF_FAR_FROM_ZERO, and TO_NEAR_INT = round(): the same function
+        return v > 0.f ? round_half_up(v) : round_half_down(v);
     }
 }
 
+// Run-time mode (warp-uniform): the four half-way modes share one branch-free body selected by two uniform flags.
 __device__ __forceinline__ int round2int_dyn(float v, int mode) {
-    switch (mode) {
-    case RND_HALF_EVEN:          return round2int<RND_HALF_EVEN>(v);
-    case RND_HALF_UP:            return round2int<RND_HALF_UP>(v);
-    case RND_HALF_DOWN:          return round2int<RND_HALF_DOWN>(v);
-    case RND_HALF_TOWARDS_ZERO:  return round2int<RND_HALF_TOWARDS_ZERO>(v);
-    case RND_HALF_FAR_FROM_ZERO: return round2int<RND_HALF_FAR_FROM_ZERO>(v);
-    case RND_UP:                 return round2int<RND_UP>(v);
-    case RND_DOWN:               return round2int<RND_DOWN>(v);
-    default:                     return round2int<RND_TO_NEAR_INT>(v);
-    }
+    if (mode == RND_HALF_EVEN) return __float2int_rn(v);
+    if (mode == RND_UP)        return __float2int_ru(v);
+    if (mode == RND_DOWN)      return __float2int_rd(v);
+    const bool pos_up = (mode != RND_HALF_DOWN) && (mode != RND_HALF_TOWARDS_ZERO);       // HALF_UP, FAR_FROM_ZERO, TO_NEAR_INT
+    const bool neg_up = (mode == RND_HALF_UP) || (mode == RND_HALF_TOWARDS_ZERO);
+    const int up = round_half_up(v), down = round_half_down(v);
+    return ((v > 0.f) ? pos_up : neg_up) ? up : down;
 }
 
 // `int o = std::round(offset)` (linear.cu:51): half away from zero, saturating.

@@ -107,6 +107,28 @@ def test_lt_all_rounding_modes_and_ranges(ext, oracle, mode):
         assert_bits_equal(y, oracle.linear_quant_t(x, s, o, lo, hi, mode), f'mode {mode} range {lo}..{hi}')
 
 
+@pytest.mark.parametrize('mode', range(8))
+def test_rounding_modes_fp32_formulation_matches_double(ext, oracle, mode):
+    """The device evaluates the "+ .5" modes in fp32 (floor/ceil + fraction test), the reference in double: same integers on the inputs
+    where the two could differ -- neighbours of every half-way point, fractions that round when subtracted, 2^23..2^31, specials."""
+    h = np.arange(-300, 300, dtype=np.float32) + np.float32(0.5)
+    near = np.concatenate([h, np.nextafter(h, np.float32(np.inf)), np.nextafter(h, np.float32(-np.inf))])
+    tiny = np.float32([-1e-30, 1e-30, -1e-45, 1e-45, -0.49999997, 0.49999997, -0.50000006, 0.50000006, -0.5, 0.5, -0.0, 0.0,
+                       -0.25 - 2.0 ** -26, -(0.5 - 2.0 ** -25), 0.5 - 2.0 ** -25, -0.99999994, 0.99999994, -1.0000001, 1.0000001])
+    big = np.float32([2 ** 23 - 0.5, 2 ** 23 + 1, 2 ** 22 + 0.5, -(2 ** 22 + 0.5), -(2 ** 23 - 0.5), 2 ** 24 + 2, 2147483520.0, -2147483520.0,
+                      2 ** 31, -2 ** 31, -2147483904.0, 3e38, -3e38, np.inf, -np.inf, np.nan, 4194303.5, -4194303.5, 8388607.5, -8388607.5])
+    r = np.random.RandomState(mode)
+    rnd = (r.standard_normal(50000) * np.exp(r.uniform(-20, 20, 50000))).astype(np.float32)
+    x = np.concatenate([near, tiny, big, rnd, -rnd])
+    for (lo, hi) in ((-2 ** 31 + 1, 2 ** 31 - 1), (-128, 127)):
+        y = ext.QuantizeTensor_LT(dev(x), t1(1.0), t1(0), lo, hi, mode)
+        assert_bits_equal(y, oracle.linear_quant_t(x, np.float32(1.0), 0, lo, hi, mode), f'mode {mode} {lo}..{hi}')
+        q = ext.QuantizeTensor_toInt(dev(x), t1(1.0), t1(0), lo, hi, -1000, mode, 32)
+        assert np.array_equal(q.cpu().numpy(), oracle.linear_quant_t(x, np.float32(1.0), 0, lo, hi, mode, return_int=True)[1]), mode
+    c = ext.QuantizeTensor_LC(dev(x[:x.size // 4 * 4]).view(4, -1), dev(np.ones(4, np.float32)), dev(np.zeros(4, np.float32)), -2 ** 31 + 1, 2 ** 31 - 1, 0, mode)
+    assert_bits_equal(c.view(-1), oracle.linear_quant_t(x[:x.size // 4 * 4], np.float32(1.0), 0, -2 ** 31 + 1, 2 ** 31 - 1, mode), f'LC mode {mode}')
+
+
 def test_lt_special_values_and_scales(ext, oracle):
     sp = np.float32([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1e-38, 3e38, -3e38, 1e20, -1e20, 2 ** 31, -2 ** 31,
                      2147483520.0, 16777217.0, 0.5, 1.5, 2.5, -0.5, 1e-30, 123456.789])
