@@ -216,6 +216,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank); sampler.start()
     barrier()
     cal.launches = 0; launches[0] = 0
+    cal.exchange_events = {}                                    # CUDA events around the two exchange steps (SURVEY 8e scaling report)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.nvtx.range_push('timed')
     t0.record(stream)
@@ -258,6 +259,8 @@ def run_ours(args, rank, world, local_rank):
         'gpu_launches': cal.launches + launches[0],
         'clocks': sampler.summary(),
         'algorithmic_gbs': round(wl.bytes_per_step() / (ms / args.steps * 1e-3) / 1e9, 1),
+        # the two exchange steps of the whole calibration (this rank's view, device time incl. waiting for the slowest rank)
+        'exchange_ms': {k: round(sum(a.elapsed_time(b) for a, b in v), 4) for k, v in cal.exchange_events.items()},
     }
     if rank == 0:
         result['fakequant'] = fakequant_sweep(ext, device, peak)

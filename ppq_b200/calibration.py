@@ -135,11 +135,27 @@ class ArenaCalibrator:
             self.ext.Histogram_T_DeviceScale(tensor, self.hist_scale[index:index + 1], True, self.hist[index])
         self.launches += 1
 
+    def _timed_exchange(self, name: str):
+        """CUDA events around one exchange step when `self.exchange_events` is a dict (bench.py's scaling report), else a no-op."""
+        import contextlib
+        ev = getattr(self, 'exchange_events', None)
+        if ev is None or not self.minmax.is_cuda: return contextlib.nullcontext()
+
+        @contextlib.contextmanager
+        def ctx():
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(torch.cuda.current_stream(self.device))
+            yield
+            b.record(torch.cuda.current_stream(self.device))
+            ev.setdefault(name, []).append((a, b))
+        return ctx()
+
     @torch.no_grad()
     def end_phase(self):
         """Exchange + render of the finished phase.  Returns True when calibration is complete."""
         if self.phase == 1:
-            allreduce_minmax(self.minmax, self.group)
+            with self._timed_exchange('minmax'):
+                allreduce_minmax(self.minmax, self.group)
             if self.method == 'minmax':
                 self.scale, self.offset = self.ext.MinMax_To_Scale_Offset(self.minmax.view(-1), self.minmax.view(-1)[1:], 2, self.quant_min,
                                                                           self.quant_max, True, self.power_of_2, self.min_scale)
@@ -149,7 +165,8 @@ class ArenaCalibrator:
             self.launches += 1
             self.phase = 2
             return False
-        allreduce_hist(self.hist, self.group)
+        with self._timed_exchange('hist'):
+            allreduce_hist(self.hist, self.group)
         self.scale, self.best_bin_range = self.ext.KL_Search(self.hist, self.bins, self.hist_scale, self.minmax, self.num_of_bits,
                                                              self.power_of_2, self.min_scale)
         self.offset = torch.zeros_like(self.scale)
