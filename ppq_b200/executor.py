@@ -233,9 +233,33 @@ class TorchExecutor:
 
 
 # ------------------------------------------------------------------------------------------------------------------ calibration drivers
+def prefetch_to_device(batches, to_device, device):
+    """Yield `to_device(batch)` for every batch with the copy of batch k+1 enqueued on a side stream before batch k is handed out, so
+    the host->device transfer of the next calibration batch (19 MB for 32 images) overlaps the forward of the current one."""
+    copy_stream = torch.cuda.Stream(device=device)
+    it = iter(batches)
+
+    def fetch():
+        x = next(it, None)
+        if x is None: return None
+        with torch.cuda.stream(copy_stream):
+            y = to_device(x)
+            done = torch.cuda.Event(); done.record(copy_stream)
+        return y, done
+
+    ahead = fetch()
+    while ahead is not None:
+        y, done = ahead
+        main = torch.cuda.current_stream(device)
+        main.wait_event(done)
+        if isinstance(y, torch.Tensor): y.record_stream(main)            # allocated on the copy stream, consumed on the main stream
+        ahead = fetch()
+        yield y
+
+
 @torch.no_grad()
 def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=None, to_device=None, deferred='auto',
-                    graphs: bool = False):
+                    graphs: bool = False, prefetch: bool = True):
     """Two-phase calibration of every observed activation through one ArenaCalibrator (statistics arena, one all-reduce per
     phase, on-device scale search).  `batches` is this rank's share of the calibration set (sample-sharded by the caller).
     deferred=False observes each tensor as the forward produces it (one launch per tensor);
@@ -255,7 +279,8 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
     mutated = None                                                        # slots whose tensors are overwritten later in the forward
     while True:
         graph = None
-        for x in batches:
+        overlapped = prefetch and to_device is not None and not graphs and dev.type == 'cuda'
+        for x in (prefetch_to_device(batches, to_device, dev) if overlapped else batches):
             if graphs:
                 if static_in is None:
                     static_in = torch.empty(x.shape, dtype=torch.float32, device=dev)
@@ -276,7 +301,7 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
                     cal.minmax.copy_(keep_mm); cal.hist.copy_(keep_h)      # capture does not execute, but stay safe
                 graph.replay()
                 continue
-            if to_device is not None: x = to_device(x)
+            if to_device is not None and not overlapped: x = to_device(x)
             if deferred is True:
                 _, tensors = executor.forward(x, collect=True)
                 cal.observe([t if t.is_contiguous() else t.contiguous() for t in tensors])

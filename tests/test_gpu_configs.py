@@ -160,6 +160,10 @@ def test_executor_calibration_paths_agree(ext):
     ex4 = build()
     cal4 = calibrate_arena(ex4, data, method='kl')                         # deferred='auto': multi-tensor launch for everything not overwritten in place
     assert torch.equal(cal4.minmax, cal.minmax) and torch.equal(cal4.hist, cal.hist) and torch.equal(cal4.scale, s1)
+    ex5 = build()                                                           # host batches, H2D of batch k+1 overlapped with forward k
+    host = [d.cpu().pin_memory() for d in data]
+    cal5 = calibrate_arena(ex5, host, method='kl', to_device=lambda t: t.to('cuda', non_blocking=True), prefetch=True)
+    assert torch.equal(cal5.minmax, cal.minmax) and torch.equal(cal5.hist, cal.hist) and torch.equal(cal5.scale, s1)
     assert all(c.state == QuantizationStates.ACTIVATED for c in ex2.observed_configs_all())
     # evaluation loop (graphwise error analysis): per-op SNR of the quantised network vs fp32, all below the reference's 0.1 bar
     from ppq_b200.executor import graphwise_error_analyse
