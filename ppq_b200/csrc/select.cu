@@ -5,9 +5,11 @@
 //   ppq_b200_isotone_t    replaces Isotone_T (sort.cu:23-40, 61-73): sorted[n-1], sorted[n-2], sorted[0], sorted[1].
 //
 // Here: MSD radix *select* on the order-preserving 32-bit key of each float (the same total order thrust's radix sort uses:
-// -NaN < -inf < ... < -0 < +0 < ... < +inf < +NaN), 11 + 11 + 10 bits, both requested ranks resolved together.  Three
+// -NaN < -inf < ... < -0 == +0 < ... < +inf < +NaN; the two zeros share one key, see order_key), 11 + 11 + 10 bits, both requested
+// ranks resolved together.  Three
 // streaming passes over the input (12 B/element, shared-memory privatised digit histograms) instead of a clone plus a full
-// device sort; no allocation -- the caller provides a small workspace.  The result is the identical element, bit for bit.
+// device sort; no allocation -- the caller provides a small workspace.  The result is the identical element, bit for bit, except that a
+// selected zero is always reported as +0.0 (equal as a float to whichever zero the reference's sort left at that index).
 #include "common.cuh"
 #include "../../include/ppq_b200.h"
 
