@@ -171,9 +171,11 @@ def test_executor_calibration_paths_agree(ext):
     assert len(report) == len(ex2.quantable_operations()) and all(0 <= v < 0.1 for v in report.values()), max(report.values())
     assert all(c.state == QuantizationStates.ACTIVATED for c in ex2.observed_configs_all())       # states restored
     # CUDA-graph replay of the whole forward (network + weight fake-quant + collectors): identical statistics
-    ex3 = build()
-    cal3 = calibrate_arena(ex3, data, method='kl', graphs=True)
-    assert torch.equal(cal3.minmax, cal.minmax) and torch.equal(cal3.hist, cal.hist) and torch.equal(cal3.scale, s1)
+    import os
+    if os.environ.get('PYTORCH_NO_CUDA_MEMORY_CACHING') != '1':            # capture needs torch's caching allocator (tools/gpu_sanitize.sh turns it off)
+        ex3 = build()
+        cal3 = calibrate_arena(ex3, data, method='kl', graphs=True)
+        assert torch.equal(cal3.minmax, cal.minmax) and torch.equal(cal3.hist, cal.hist) and torch.equal(cal3.scale, s1)
     # quantised forward runs and differs from fp32 only by quantisation noise
     x = data[0]
     yq = ex2.forward(x)
