@@ -21,7 +21,8 @@ constexpr int kDigits = 2048;                  // 11-bit digits (the last pass u
 struct SelectState {                           // lives in the caller's workspace
     unsigned long long hist[2][kDigits];       // per rank: digit histogram of the current pass
     unsigned int prefix[2];                    // key bits resolved so far (high bits)
-    unsigned int pad_[2];
+    unsigned int done;                         // CTAs that have flushed their digits in the current pass
+    unsigned int pad_;
     long long rank[2];                         // remaining rank inside the current prefix bucket
     long long ranks_in[4];
 };
@@ -39,55 +40,13 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 
 __global__ void select_init_kernel(SelectState *st, long long r0, long long r1) {
     for (int i = threadIdx.x; i < 2 * kDigits; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
-    if (threadIdx.x == 0) { st->prefix[0] = st->prefix[1] = 0u; st->rank[0] = r0; st->rank[1] = r1; }
+    if (threadIdx.x == 0) { st->prefix[0] = st->prefix[1] = 0u; st->done = 0u; st->rank[0] = r0; st->rank[1] = r1; }
 }
 
-// PASS 0: digit = key[31:21];  PASS 1: key[20:10] among keys whose top 11 bits match;  PASS 2: key[9:0] among top-22 matches.
+// Block-wide prefix sum over the digit histogram of each rank (2 digits per thread, warp shuffles): pick the digit bucket that contains
+// the rank, extend the prefix, clear the histograms for the next pass.  Run by the LAST CTA of a pass to finish its flush (1024 threads).
 template <int PASS>
-__global__ void __launch_bounds__(kSelThreads)
-select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restrict__ st) {
-    __shared__ int sh[2][kDigits + 32];                            // + a trash slot per rank: the shared red is unconditional (cf. collectors.cu)
-    for (int i = threadIdx.x; i < 2 * (kDigits + 32); i += kSelThreads) (&sh[0][0])[i] = 0;
-    __syncthreads();
-    constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
-    constexpr uint32_t dmask = PASS == 2 ? 0x3FFu : 0x7FFu;
-    constexpr uint32_t pmask = PASS == 0 ? 0u : (PASS == 1 ? 0xFFE00000u : 0xFFFFFC00u);
-    const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
-    const bool same = (p0 == p1);
-    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(&sh[0][0]), a1 = (uint32_t)__cvta_generic_to_shared(&sh[1][0]);
-    auto visit = [&](float v) {
-        const uint32_t k = order_key(v);
-        const uint32_t hi = k & pmask, d = (k >> shift) & dmask;
-        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + ((hi == p0) ? d : (uint32_t)kDigits) * 4u) : "memory");
-        if (!same) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1 + ((hi == p1) ? d : (uint32_t)kDigits) * 4u) : "memory");
-    };
-    const int64_t first = (int64_t)blockIdx.x * kSelThreads + threadIdx.x, stride = (int64_t)gridDim.x * kSelThreads;
-    if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
-        const int64_t n4 = n >> 2;
-        const float4 *x4 = reinterpret_cast<const float4 *>(x);
-        for (int64_t i = first; i < n4; i += 4 * stride) {
-            float4 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (i + j * stride < n4) v[j] = ld_stream4(x4 + i + j * stride);
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (i + j * stride < n4) { visit(v[j].x); visit(v[j].y); visit(v[j].z); visit(v[j].w); }
-        }
-        const int64_t t = (n4 << 2) + first;
-        if (t < n) visit(x[t]);
-    } else {
-        for (int64_t i = first; i < n; i += stride) visit(ld_stream1(x + i));
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kDigits; i += kSelThreads) {
-        if (sh[0][i]) atomicAdd(&st->hist[0][i], (unsigned long long)sh[0][i]);
-        if (!same && sh[1][i]) atomicAdd(&st->hist[1][i], (unsigned long long)sh[1][i]);
-    }
-}
-
-// One 1024-thread CTA: block-wide prefix sum over the digit histogram of each rank (2 digits per thread, warp shuffles), pick the
-// digit bucket that contains the rank, extend the prefix, clear the histograms for the next pass.
-template <int PASS>
-__global__ void __launch_bounds__(1024) select_scan_kernel(SelectState *st, float *out, int out_stride) {
+__device__ __forceinline__ void select_scan(SelectState *st, float *out, int out_stride) {
     constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
     __shared__ unsigned long long warp_tot[32];
     __shared__ unsigned int new_prefix[2];
@@ -97,7 +56,7 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(SelectState *st, floa
     for (int r = 0; r < 2; r++) {
         const unsigned long long *h = st->hist[(r == 1 && same) ? 0 : r];
         const long long k = st->rank[r];
-        const unsigned long long c0 = h[2 * t], c1 = h[2 * t + 1];
+        const unsigned long long c0 = __ldcg(h + 2 * t), c1 = __ldcg(h + 2 * t + 1);        // written by other CTAs' atomics: read at L2
         unsigned long long incl = c0 + c1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
@@ -112,11 +71,76 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(SelectState *st, floa
         }
         __syncthreads();
     }
-    for (int i = t; i < 2 * kDigits; i += 1024) (&st->hist[0][0])[i] = 0ull;
+    for (int i = t; i < 2 * kDigits; i += kSelThreads) (&st->hist[0][0])[i] = 0ull;
     if (t < 2) {
         st->prefix[t] = new_prefix[t];
         st->rank[t] = new_rank[t];
         if (PASS == 2) out[t * out_stride] = key_to_float(new_prefix[t]);
+    }
+    if (t == 0) st->done = 0u;
+}
+
+// PASS 0: digit = key[31:21];  PASS 1: key[20:10] among keys whose top 11 bits match;  PASS 2: key[9:0] among top-22 matches.
+// Pass 0 is a histogram of every element (unconditional shared red, as in collectors.cu).  In passes 1 and 2 only the elements of the
+// one or two buckets chosen so far count: a vector whose four keys all miss both prefixes -- the common case, the requested ranks sit
+// in the tails -- costs four masked compares and no shared-memory traffic, so these passes stream like the min/max collector.
+template <int PASS>
+__global__ void __launch_bounds__(kSelThreads)
+select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restrict__ st, float *out, int out_stride) {
+    __shared__ int sh[2][kDigits];
+    __shared__ bool is_last;
+    for (int i = threadIdx.x; i < 2 * kDigits; i += kSelThreads) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
+    constexpr uint32_t dmask = PASS == 2 ? 0x3FFu : 0x7FFu;
+    constexpr uint32_t pmask = PASS == 0 ? 0u : (PASS == 1 ? 0xFFE00000u : 0xFFFFFC00u);
+    const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
+    const bool same = (p0 == p1);
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(&sh[0][0]), a1 = (uint32_t)__cvta_generic_to_shared(&sh[1][0]);
+    auto count = [&](uint32_t k) {
+        const uint32_t hi = k & pmask, d = (k >> shift) & dmask;
+        if (PASS == 0) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + d * 4u) : "memory"); return; }
+        if (hi == p0) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + d * 4u) : "memory");
+        if (!same && hi == p1) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1 + d * 4u) : "memory");
+    };
+    auto visit4 = [&](const float4 &v) {
+        const uint32_t k0 = order_key(v.x), k1 = order_key(v.y), k2 = order_key(v.z), k3 = order_key(v.w);
+        if (PASS != 0) {
+            const bool any = ((k0 & pmask) == p0) | ((k1 & pmask) == p0) | ((k2 & pmask) == p0) | ((k3 & pmask) == p0) |
+                             ((k0 & pmask) == p1) | ((k1 & pmask) == p1) | ((k2 & pmask) == p1) | ((k3 & pmask) == p1);
+            if (!any) return;
+        }
+        count(k0); count(k1); count(k2); count(k3);
+    };
+    const int64_t first = (int64_t)blockIdx.x * kSelThreads + threadIdx.x, stride = (int64_t)gridDim.x * kSelThreads;
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+        const int64_t n4 = n >> 2;
+        const float4 *x4 = reinterpret_cast<const float4 *>(x);
+        for (int64_t i = first; i < n4; i += 4 * stride) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (i + j * stride < n4) v[j] = ld_stream4(x4 + i + j * stride);
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (i + j * stride < n4) visit4(v[j]);
+        }
+        const int64_t t = (n4 << 2) + first;
+        if (t < n) count(order_key(x[t]));
+    } else {
+        for (int64_t i = first; i < n; i += stride) count(order_key(ld_stream1(x + i)));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kDigits; i += kSelThreads) {
+        if (sh[0][i]) atomicAdd(&st->hist[0][i], (unsigned long long)sh[0][i]);
+        if (!same && sh[1][i]) atomicAdd(&st->hist[1][i], (unsigned long long)sh[1][i]);
+    }
+    // the last CTA to get here resolves the pass (no separate scan launch): every CTA's atomics are ordered before its ticket
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->done, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        select_scan<PASS>(st, out, out_stride);
     }
 }
 
@@ -125,12 +149,9 @@ static int select_two(const float *x, int64_t n, long long r0, long long r1, flo
     if (g > kSMs) g = kSMs;
     if (g < 1) g = 1;
     select_init_kernel<<<1, 1024, 0, s>>>(st, r0, r1);
-    select_hist_kernel<0><<<(int)g, kSelThreads, 0, s>>>(x, n, st);
-    select_scan_kernel<0><<<1, 1024, 0, s>>>(st, out, out_stride);
-    select_hist_kernel<1><<<(int)g, kSelThreads, 0, s>>>(x, n, st);
-    select_scan_kernel<1><<<1, 1024, 0, s>>>(st, out, out_stride);
-    select_hist_kernel<2><<<(int)g, kSelThreads, 0, s>>>(x, n, st);
-    select_scan_kernel<2><<<1, 1024, 0, s>>>(st, out, out_stride);
+    select_hist_kernel<0><<<(int)g, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
+    select_hist_kernel<1><<<(int)g, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
+    select_hist_kernel<2><<<(int)g, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
     return (int)cudaGetLastError();
 }
 
