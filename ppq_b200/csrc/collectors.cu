@@ -262,8 +262,8 @@ __device__ __forceinline__ void hist_stream(const float *__restrict__ x, int64_t
 
 constexpr int kHistThreads = 1024;   // one big CTA per SM: the flush of the private bins (bins global atomics per CTA) is what
                                      // limits small-CTA configurations (measured: 256 thr x 8/SM 59 % -> 1024 thr x 1/SM 82 % of HBM peak)
-template <int VARIANT, class Bin, int U = kUnroll, int TPB = kHistThreads>
-__global__ void __launch_bounds__(TPB)
+template <int VARIANT, class Bin, int U = kUnroll, int TPB = kHistThreads, int MINB = 1>
+__global__ void __launch_bounds__(TPB, MINB)
 histogram_kernel(const float *__restrict__ x, int64_t n, BinParams bp, int32_t *__restrict__ hist) {
     extern __shared__ int sh[];
     const int bins = bp.bins;
@@ -370,6 +370,9 @@ static int launch_hist(const float *x, int64_t n, const BinParams &bin, int64_t 
     case 2:  histogram_kernel<2, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     case 3:  histogram_kernel<3, Bin, kUnroll, kThreads><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
     case 4:  histogram_kernel<0, Bin, 8, kThreads><<<grid * 8 > kSMs * 8 ? kSMs * 8 : grid * 8, kThreads, smem, st>>>(x, n, bin, hist); break;   // the round-1 small-CTA layout
+    // 5 / 6: two 1024-thread CTAs per SM (32 registers per thread), 2 / 4 loads in flight per thread
+    case 5:  histogram_kernel<0, Bin, 2, kHistThreads, 2><<<grid * 2 > kSMs * 2 ? kSMs * 2 : grid * 2, kHistThreads, smem, st>>>(x, n, bin, hist); break;
+    case 6:  histogram_kernel<0, Bin, 4, kHistThreads, 2><<<grid * 2 > kSMs * 2 ? kSMs * 2 : grid * 2, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     default: histogram_kernel<0, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     }
     return (int)cudaGetLastError();

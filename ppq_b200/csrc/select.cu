@@ -85,7 +85,7 @@ __device__ __forceinline__ void select_scan(SelectState *st, float *out, int out
 // one or two buckets chosen so far count: a vector whose four keys all miss both prefixes -- the common case, the requested ranks sit
 // in the tails -- costs four masked compares and no shared-memory traffic, so these passes stream like the min/max collector.
 template <int PASS>
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __launch_bounds__(kSelThreads, PASS == 0 ? 2 : 1)
 select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restrict__ st, float *out, int out_stride) {
     __shared__ int sh[2][kDigits];
     __shared__ bool is_last;
@@ -103,25 +103,28 @@ select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restri
         if (hi == p0) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + d * 4u) : "memory");
         if (!same && hi == p1) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1 + d * 4u) : "memory");
     };
+    // Fast rejection on the RAW bits (passes 1-2): key & pmask == p  <=>  bits & pmask == raw(p), because the key transform only depends on
+    // the sign, which the prefix fixes.  -0.0 is the one exception (its key is +0's): when a prefix is the bucket of +0 the raw pattern of
+    // -0.0 is accepted too; a false positive only costs the exact test in count().  One AND + three compares per element.
+    auto raw_of = [&](uint32_t p) { return (p & 0x80000000u) ? (p & 0x7FFFFFFFu) : (~p & pmask); };
+    const uint32_t c0 = raw_of(p0), c1 = raw_of(p1), c2 = (p0 == 0x80000000u || p1 == 0x80000000u) ? 0x80000000u : c0;
+    auto hit = [&](float f) { const uint32_t t = __float_as_uint(f) & pmask; return (t == c0) | (t == c1) | (t == c2); };
     auto visit4 = [&](const float4 &v) {
-        const uint32_t k0 = order_key(v.x), k1 = order_key(v.y), k2 = order_key(v.z), k3 = order_key(v.w);
-        if (PASS != 0) {
-            const bool any = ((k0 & pmask) == p0) | ((k1 & pmask) == p0) | ((k2 & pmask) == p0) | ((k3 & pmask) == p0) |
-                             ((k0 & pmask) == p1) | ((k1 & pmask) == p1) | ((k2 & pmask) == p1) | ((k3 & pmask) == p1);
-            if (!any) return;
-        }
-        count(k0); count(k1); count(k2); count(k3);
+        if (PASS != 0 && !(hit(v.x) | hit(v.y) | hit(v.z) | hit(v.w))) return;
+        count(order_key(v.x)); count(order_key(v.y)); count(order_key(v.z)); count(order_key(v.w));
     };
     const int64_t first = (int64_t)blockIdx.x * kSelThreads + threadIdx.x, stride = (int64_t)gridDim.x * kSelThreads;
     if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
         const int64_t n4 = n >> 2;
         const float4 *x4 = reinterpret_cast<const float4 *>(x);
-        for (int64_t i = first; i < n4; i += 4 * stride) {
-            float4 v[4];
+        // passes 1-2 have no shared-memory traffic to overlap with: 8 loads in flight per thread instead of 4 (one 1024-thread CTA per SM)
+        constexpr int U = PASS == 0 ? 4 : 8;
+        for (int64_t i = first; i < n4; i += U * stride) {
+            float4 v[U];
 #pragma unroll
-            for (int j = 0; j < 4; j++) if (i + j * stride < n4) v[j] = ld_stream4(x4 + i + j * stride);
+            for (int j = 0; j < U; j++) if (i + j * stride < n4) v[j] = ld_stream4(x4 + i + j * stride);
 #pragma unroll
-            for (int j = 0; j < 4; j++) if (i + j * stride < n4) visit4(v[j]);
+            for (int j = 0; j < U; j++) if (i + j * stride < n4) visit4(v[j]);
         }
         const int64_t t = (n4 << 2) + first;
         if (t < n) count(order_key(x[t]));
@@ -149,7 +152,11 @@ static int select_two(const float *x, int64_t n, long long r0, long long r1, flo
     if (g > kSMs) g = kSMs;
     if (g < 1) g = 1;
     select_init_kernel<<<1, 1024, 0, s>>>(st, r0, r1);
-    select_hist_kernel<0><<<(int)g, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
+    // pass 0 needs 32 registers per thread: two 1024-thread CTAs fit on an SM (passes 1-2 trade that for 8 loads in flight per thread)
+    int64_t g0 = (n + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
+    if (g0 > 2 * kSMs) g0 = 2 * kSMs;
+    if (g0 < 1) g0 = 1;
+    select_hist_kernel<0><<<(int)g0, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
     select_hist_kernel<1><<<(int)g, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
     select_hist_kernel<2><<<(int)g, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
     return (int)cudaGetLastError();

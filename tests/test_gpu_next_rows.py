@@ -47,9 +47,10 @@ def close(a, b, rtol=1e-4, atol=1e-6):
 def test_quantile_vs_sort_oracle_and_reference(ext, ref, oracle):
     g = torch.Generator(device='cuda').manual_seed(0)
     for n in (1, 2, 3, 17, 1000, 4099, 401408, (1 << 21) + 5):
-        for kind in ('randn', 'relu', 'const', 'ints'):
+        for kind in ('randn', 'relu', 'negrelu', 'const', 'ints'):
             x = torch.randn(n, device='cuda', generator=g) * 3
             if kind == 'relu': x = torch.relu(x)
+            if kind == 'negrelu': x = -torch.relu(x)                              # half of the elements are -0.0: the bucket of +0 must take them
             if kind == 'const': x = torch.full((n,), -1.25, device='cuda')
             if kind == 'ints': x = torch.randint(-5, 5, (n,), device='cuda', generator=g).float()
             if n > 8: x[3] = -0.0; x[5] = 0.0
