@@ -463,6 +463,8 @@ int ppq_b200_linear_quant_t(const float *x, float *y, int64_t n, const float *sc
         }
         return launch_tensor<LinearOp<0>, float>(x, y, n, scale, offset, {qmin, qmax, 0}, st);
     }
+    if (rounding == RND_HALF_UP)              // the one other policy a shipped quantizer selects (NXPQuantizer.py:122): compile-time mode as well
+        return launch_tensor<LinearOp<RND_HALF_UP>, float>(x, y, n, scale, offset, {qmin, qmax, RND_HALF_UP}, st);
     return launch_tensor<LinearOp<-1>, float>(x, y, n, scale, offset, {qmin, qmax, rounding}, st);
 }
 
@@ -472,6 +474,8 @@ int ppq_b200_linear_quant_c(const float *x, float *y, int64_t n, int64_t epc, in
     if (qmin > qmax) return (int)cudaErrorInvalidValue;
     if (rounding == RND_HALF_EVEN)
         return launch_channel<LinearOp<0>, float>(x, y, n, epc, C, scale, offset, {qmin, qmax, 0}, st);
+    if (rounding == RND_HALF_UP)
+        return launch_channel<LinearOp<RND_HALF_UP>, float>(x, y, n, epc, C, scale, offset, {qmin, qmax, RND_HALF_UP}, st);
     return launch_channel<LinearOp<-1>, float>(x, y, n, epc, C, scale, offset, {qmin, qmax, rounding}, st);
 }
 

@@ -80,7 +80,8 @@ def main():
             ext.set_variant('linear_quant_t', var)
             report(f'linear_quant_t var{var}', timeit(lambda i: ext.QuantizeTensor_LT(xs[i], one, zero, -128, 127, 0), args.reps, nbuf), 8)
         ext.set_variant('linear_quant_t', 0)
-        report('linear_quant_t mode1 (dyn rounding)', timeit(lambda i: ext.QuantizeTensor_LT(xs[i], one, zero, -128, 127, 1), args.reps, nbuf), 8)
+        report('linear_quant_t ROUND_HALF_UP (compile-time mode)', timeit(lambda i: ext.QuantizeTensor_LT(xs[i], one, zero, -128, 127, 1), args.reps, nbuf), 8)
+        report('linear_quant_t ROUND_HALF_FAR_FROM_ZERO (run-time mode)', timeit(lambda i: ext.QuantizeTensor_LT(xs[i], one, zero, -128, 127, 4), args.reps, nbuf), 8)
         report('linear_quant_t toInt8', timeit(lambda i: ext.QuantizeTensor_toInt(xs[i], one, zero, -128, 127, -1000, 0, 8), args.reps, nbuf), 5)
     if 'quantile' in only:
         report('quantile_t q=0.9999 (3-pass radix select, 12 B/elem)', timeit(lambda i: ext.Quantile_T(xs[i], 0.9999), args.reps, nbuf), 12)
