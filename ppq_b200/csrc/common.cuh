@@ -75,6 +75,15 @@ __device__ __forceinline__ int offset_to_int(float o) { return __float2int_rz(ro
 // Out-of-line IEEE division: keeps the ~25-instruction div.rn expansion (and its slow-path call) out of the hot loops.
 static __device__ __noinline__ float ieee_div_slow(float x, float s) { return __fdiv_rn(x, s); }
 
+// max(|a|, |b|, |c|, |d|), NaN if any lane is NaN
+__device__ __forceinline__ float max_abs_nan4(const float4 &q) {
+    float m, n;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(m) : "f"(fabsf(q.x)), "f"(fabsf(q.y)));
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(n) : "f"(fabsf(q.z)), "f"(fabsf(q.w)));
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(m) : "f"(m), "f"(n));
+    return m;
+}
+
 struct ExactDiv {
     float s, r;
     __device__ __forceinline__ ExactDiv() {}
@@ -100,13 +109,11 @@ struct ExactDiv {
         if (!(fabsf(q) < limit)) q = ieee_div_slow(x, s);
         return q;
     }
-    // Four quotients, one range test: |q| bit patterns order like unsigned integers and every NaN sorts above +inf,
-    // so max(|bits|) >= bits(limit) catches huge, infinite and NaN lanes with three integer max and one compare.
+    // Four quotients, one range test: the NaN-propagating maximum of the four magnitudes (three FMNMX.NAN with |.| operand
+    // modifiers) fails `< limit` for huge, infinite and NaN lanes alike.
     __device__ __forceinline__ float4 div4(const float4 &x, float limit = 2147483648.f) const {
         float4 q = make_float4(fast(x.x), fast(x.y), fast(x.z), fast(x.w));
-        const uint32_t m = max(max(__float_as_uint(q.x) & 0x7FFFFFFFu, __float_as_uint(q.y) & 0x7FFFFFFFu),
-                               max(__float_as_uint(q.z) & 0x7FFFFFFFu, __float_as_uint(q.w) & 0x7FFFFFFFu));
-        if (m >= __float_as_uint(limit)) {
+        if (!(max_abs_nan4(q) < limit)) {
             q.x = ieee_div_slow(x.x, s); q.y = ieee_div_slow(x.y, s); q.z = ieee_div_slow(x.z, s); q.w = ieee_div_slow(x.w, s);
         }
         return q;
@@ -117,9 +124,7 @@ struct ExactDiv {
 __device__ __forceinline__ float4 exact_div4x(const ExactDiv &a, const ExactDiv &b, const ExactDiv &c, const ExactDiv &d,
                                               const float4 &x, float limit = 2147483648.f) {
     float4 q = make_float4(a.fast(x.x), b.fast(x.y), c.fast(x.z), d.fast(x.w));
-    const uint32_t m = max(max(__float_as_uint(q.x) & 0x7FFFFFFFu, __float_as_uint(q.y) & 0x7FFFFFFFu),
-                           max(__float_as_uint(q.z) & 0x7FFFFFFFu, __float_as_uint(q.w) & 0x7FFFFFFFu));
-    if (m >= __float_as_uint(limit)) {
+    if (!(max_abs_nan4(q) < limit)) {
         q.x = ieee_div_slow(x.x, a.s); q.y = ieee_div_slow(x.y, b.s); q.z = ieee_div_slow(x.z, c.s); q.w = ieee_div_slow(x.w, d.s);
     }
     return q;

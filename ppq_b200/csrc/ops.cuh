@@ -65,7 +65,7 @@ struct FloatOp {
     struct Params { int E, M, mode; float cmin, cmax; };
     static constexpr bool kLight = FAST;
     struct Plan {
-        float hi, lo, cmin, cmax, min_sub, inv_min_sub, sub_magic;
+        float hi, lo, cmin, cmax, min_sub, inv_min_sub, sub_magic, sub_thresh;
         uint32_t sub_thresh_bits, half_minus1, keep_mask; int M, mode;
         __device__ __forceinline__ explicit Plan(const Params &p) : cmin(p.cmin), cmax(p.cmax), M(p.M), mode(p.mode) {
             const int emin = -(1 << (p.E - 1)) + 1, emax = 1 << (p.E - 1);
@@ -78,6 +78,7 @@ struct FloatOp {
             inv_min_sub = __uint_as_float((uint32_t)(127 + k) << 23);                   // u / 2^-k == u * 2^k exactly
             sub_magic = __uint_as_float(((uint32_t)(127 + 23 - k) << 23) | 0x00400000u);  // 1.5 * 2^(23-k): ulp == 2^-k
             sub_thresh_bits = (uint32_t)(emin + 1 + 127) << 23;                         // |u| < 2^(emin+1) -> subnormal grid
+            sub_thresh = __uint_as_float(sub_thresh_bits);
             half_minus1 = (1u << (22 - p.M)) - 1u;
             keep_mask = ~((1u << (23 - p.M)) - 1u);
         }
@@ -90,15 +91,16 @@ struct FloatOp {
     __device__ __forceinline__ float grid(float u) const {
         if constexpr (FAST) {
             {
-                const float uc = fmin_nan(fmax_nan(u, pl.lo), pl.hi);                   // NaN stays NaN (canonical), like the comparisons upstream
-                const uint32_t b = __float_as_uint(uc), mag = b & 0x7FFFFFFFu;
+                const float uc = fmin_nan(fmax_nan(u, pl.lo), pl.hi);                   // NaN stays NaN (canonical 0x7FFFFFFF), like the comparisons upstream
                 // normal range: round the magnitude's discarded mantissa bits half-DOWN (an exact tie keeps the lower value,
-                // because rint(0.5) == 0 upstream); the carry may bump the exponent
-                const uint32_t nb = ((mag + pl.half_minus1) & pl.keep_mask) + (b & 0x80000000u);
+                // because rint(0.5) == 0 upstream); the carry may bump the exponent.  Adding to the signed pattern is the same as
+                // adding to the magnitude: a clamped finite value cannot carry into bit 31, and the canonical NaN has sign 0
+                // (its carry into bit 31 reproduces the reference's -0.0 for NaN).
+                const uint32_t nb = (__float_as_uint(uc) + pl.half_minus1) & pl.keep_mask;
                 // subnormal range: ties-to-even on the 2^-k grid, computed with the add-magic-constant trick (sign of zero lost,
                 // exactly like the int round trip upstream)
                 const float sub = __fsub_rn(__fadd_rn(uc, pl.sub_magic), pl.sub_magic);
-                return mag < pl.sub_thresh_bits ? sub : __uint_as_float(nb);
+                return fabsf(uc) < pl.sub_thresh ? sub : __uint_as_float(nb);            // false for NaN -> nb, as with the integer compare
             }
         }
         if (u > pl.hi) return pl.hi;
