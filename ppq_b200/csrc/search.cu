@@ -80,6 +80,7 @@ __global__ void hist_scale_kernel(const float *__restrict__ minmax, int64_t coun
 
 // ---- KL search: one CTA per histogram ---------------------------------------------------------------------------------------
 constexpr int kKlThreads = 512;
+constexpr int kKlMemoBins = 8192;             // up to here the memoised logarithms fit next to the histogram and its prefix sums
 
 __device__ __forceinline__ double block_sum(double v, double *scratch) {
 #pragma unroll
@@ -99,7 +100,14 @@ kl_search_kernel(const int32_t *__restrict__ hist_arena, int bins, const float *
     extern __shared__ unsigned char kl_smem[];
     float *h = reinterpret_cast<float *>(kl_smem);                    // [bins]   the edited histogram as fp32
     double *pre = reinterpret_cast<double *>(kl_smem + (((size_t)bins * 4 + 7) & ~(size_t)7));   // [bins + 1] exclusive prefix sums
-    float *gval = reinterpret_cast<float *>(pre + bins + 1);          // [quant_bins] per-group spread value
+    float *gval = reinterpret_cast<float *>(pre + bins + 1);          // [quant_bins] per-group spread value, then q of the group
+    // memo (bins <= kKlMemoBins): log10(p + 1e-30) of every bin is the same for all 32 candidates (only the bin that absorbs the tail
+    // differs), and log10(q + 1e-30) is shared by the bins of a group -> 4096 + 32 x 128 fp64 logarithms instead of 2 x 67 584.
+    // The doubles that enter the sum are the same ones, in the same order, so the losses are bit-identical to the direct evaluation.
+    const bool memo = bins <= kKlMemoBins;
+    double *glogq = reinterpret_cast<double *>(kl_smem + ((((size_t)bins * 4 + 7) & ~(size_t)7) + (size_t)(bins + 1) * 8 +
+                                                          (((size_t)(1 << (num_of_bits - 1)) * 4 + 7) & ~(size_t)7)));   // [quant_bins]
+    double *logp = glogq + (1 << (num_of_bits - 1));                                                                    // [bins]
     __shared__ double scratch[kKlThreads / 32];
     __shared__ double s_best_loss; __shared__ int s_best;
 
@@ -135,6 +143,7 @@ kl_search_kernel(const int32_t *__restrict__ hist_arena, int bins, const float *
     }
     const float total = (float)pre[bins];                            // torch.sum(histogram) (fp32 tensor)
     if (threadIdx.x == 0) { s_best_loss = 0.0; s_best = -1; }
+    if (memo) for (int i = threadIdx.x; i < bins; i += kKlThreads) logp[i] = log10((double)__fdiv_rn(h[i], total) + 1e-30);
 
     for (int br = quant_bins; br < bins + quant_bins - 1; br += quant_bins) {
         if (br > bins) break;                                         // range() upstream never exceeds bins for bins % quant_bins == 0
@@ -153,16 +162,28 @@ kl_search_kernel(const int32_t *__restrict__ hist_arena, int bins, const float *
         for (int i = threadIdx.x; i < br; i += kKlThreads) if (h[i] > 0.f) qs += (double)gval[i / ratio];
         const float qsum = (float)block_sum(qs, scratch);
         const float tail = (float)(pre[bins] - pre[br]);              // torch.sum(histogram[bin_range:])
+        // q = (spread value * non-empty mask) / sum: when every bin of the candidate is empty this is 0/0 = NaN upstream
+        // and the candidate's loss is NaN (python's sorted() then keeps that first candidate in front) -- keep that.
+        const float q_empty = __fdiv_rn(0.f, qsum);
+        if (memo) {
+            for (int g = threadIdx.x; g < quant_bins; g += kKlThreads) {
+                const float q = __fdiv_rn(gval[g], qsum);
+                gval[g] = q;                                          // every thread is past its last read of the spread values (block_sum)
+                glogq[g] = log10((double)q + 1e-30);
+            }
+            __syncthreads();
+        }
         double kl = 0.0;
         for (int i = threadIdx.x; i < br; i += kKlThreads) {
             float pv = h[i];
-            if (i == br - 1) pv = __fadd_rn(pv, tail);
+            const bool nonempty = pv > 0.f, last = (i == br - 1);
+            if (last) pv = __fadd_rn(pv, tail);
             const float p = __fdiv_rn(pv, total);
-            // q = (spread value * non-empty mask) / sum: when every bin of the candidate is empty this is 0/0 = NaN upstream
-            // and the candidate's loss is NaN (python's sorted() then keeps that first candidate in front) -- keep that.
-            const float q = __fdiv_rn(h[i] > 0.f ? gval[i / ratio] : 0.f, qsum);
+            const float q = nonempty ? (memo ? gval[i / ratio] : __fdiv_rn(gval[i / ratio], qsum)) : q_empty;
             if (p == 0.f && q == q) continue;                         // 0 * (finite) contributes exactly 0
-            kl += (double)p * (log10((double)p + 1e-30) - log10((double)q + 1e-30));
+            const double lp = (memo && !last) ? logp[i] : log10((double)p + 1e-30);
+            const double lq = (memo && nonempty) ? glogq[i / ratio] : log10((double)q + 1e-30);
+            kl += (double)p * (lp - lq);
         }
         kl = block_sum(kl, scratch);
         if (threadIdx.x == 0 && (s_best < 0 || kl < s_best_loss)) { s_best = br; s_best_loss = kl; }
@@ -286,7 +307,8 @@ int ppq_b200_kl_search(const int32_t *hist_arena, int64_t count, int64_t bins, c
     if (num_of_bits < 2 || num_of_bits > 16) return (int)cudaErrorInvalidValue;
     const int64_t qb = 1ll << (num_of_bits - 1);
     if (bins < qb || bins > 16384 || bins < kKlThreads) return (int)cudaErrorInvalidValue;
-    const size_t smem = (((size_t)bins * 4 + 7) & ~(size_t)7) + (size_t)(bins + 1) * 8 + (size_t)qb * 4;
+    size_t smem = (((size_t)bins * 4 + 7) & ~(size_t)7) + (size_t)(bins + 1) * 8 + (((size_t)qb * 4 + 7) & ~(size_t)7);
+    if (bins <= kKlMemoBins) smem += (size_t)(qb + bins) * 8;          // memoised logarithms (see the kernel)
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(kl_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);

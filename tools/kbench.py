@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel micro-benchmarks (CUDA events, rotating buffers > L2) used to choose variants and to feed ncu.
 
-    python tools/kbench.py [--only hist,lt,lc,ft,minmax,multi,quantile,ltshape] [--reps 20]
+    python tools/kbench.py [--only hist,lt,lc,ft,minmax,multi,quantile,kl,ltshape] [--reps 20]
 """
 import argparse
 import ctypes
@@ -95,6 +95,12 @@ def main():
             secs = timeit(lambda i: ext.QuantizeTensor_LC(vs[i], s, o, -128, 127, axis, 0), args.reps, nbuf)
             gbs = 8 * m / secs / 1e9
             print(f'{"linear_quant_c " + str(shape) + " axis " + str(axis):48s} {secs*1e6:9.1f} us  {gbs:8.1f} GB/s  {gbs/PEAK:6.1%}', flush=True)
+    if 'kl' in only:
+        for T in (1, 106):
+            hist = torch.poisson(torch.full((T, 4096), 50.0, device=dev) * torch.linspace(2, 0.01, 4096, device=dev)).to(torch.int32)
+            hs = torch.full((T,), 0.001, device=dev)
+            secs = timeit(lambda i: ext.KL_Search(hist, 4096, hs, None, 8, False, 1e-8), args.reps, 1)
+            print(f'{"kl_search " + str(T) + " x 4096-bin histograms":48s} {secs*1e6:9.1f} us', flush=True)
     if 'multi' in only:
         # every Conv/Linear weight of a network in one launch; copies of the table rotate so that the weights come from HBM, not L2
         import torchvision
