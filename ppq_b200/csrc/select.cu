@@ -43,35 +43,39 @@ __global__ void select_init_kernel(SelectState *st, long long r0, long long r1) 
     if (threadIdx.x == 0) { st->prefix[0] = st->prefix[1] = 0u; st->done = 0u; st->rank[0] = r0; st->rank[1] = r1; }
 }
 
-// Block-wide prefix sum over the digit histogram of each rank (2 digits per thread, warp shuffles): pick the digit bucket that contains
-// the rank, extend the prefix, clear the histograms for the next pass.  Run by the LAST CTA of a pass to finish its flush (1024 threads).
-template <int PASS>
-__device__ __forceinline__ void select_scan(SelectState *st, float *out, int out_stride) {
+// Block-wide prefix sum over the digit histogram of each rank (kDigits / TPB consecutive digits per thread, warp shuffles): pick the digit
+// bucket that contains the rank, extend the prefix, clear the histograms for the next pass.  Run by the LAST CTA of a pass to finish its flush.
+template <int PASS, int TPB>
+__device__ __noinline__ void select_scan(SelectState *st, float *out, int out_stride) {
     constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
-    __shared__ unsigned long long warp_tot[32];
+    constexpr int D = kDigits / TPB;                                    // digits per thread: 2 (1024 threads) or 8 (256 threads)
+    __shared__ unsigned long long warp_tot[TPB / 32];
     __shared__ unsigned int new_prefix[2];
     __shared__ long long new_rank[2];
     const bool same = st->prefix[0] == st->prefix[1];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     for (int r = 0; r < 2; r++) {
         const unsigned long long *h = st->hist[(r == 1 && same) ? 0 : r];
-        const long long k = st->rank[r];
-        const unsigned long long c0 = __ldcg(h + 2 * t), c1 = __ldcg(h + 2 * t + 1);        // written by other CTAs' atomics: read at L2
-        unsigned long long incl = c0 + c1;
+        const unsigned long long k = (unsigned long long)st->rank[r];
+        unsigned long long c[D], mine = 0;
+#pragma unroll
+        for (int j = 0; j < D; j++) { c[j] = __ldcg(h + D * t + j); mine += c[j]; }        // written by other CTAs' atomics: read at L2
+        unsigned long long incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
         if (lane == 31) warp_tot[w] = incl;
         __syncthreads();
-        unsigned long long before = incl - (c0 + c1);
+        unsigned long long before = incl - mine;
         for (int i = 0; i < w; i++) before += warp_tot[i];
-        // the bucket d with  before(d) <= k < before(d) + count(d); ranks are always < total, so exactly one thread matches
-        if ((unsigned long long)k >= before && (unsigned long long)k < before + c0) { new_prefix[r] = st->prefix[r] | ((unsigned int)(2 * t) << shift); new_rank[r] = k - (long long)before; }
-        else if ((unsigned long long)k >= before + c0 && (unsigned long long)k < before + c0 + c1) {
-            new_prefix[r] = st->prefix[r] | ((unsigned int)(2 * t + 1) << shift); new_rank[r] = k - (long long)(before + c0);
+        // the bucket d with  before(d) <= k < before(d) + count(d); ranks are always < total, so exactly one (thread, digit) matches
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            if (k >= before && k < before + c[j]) { new_prefix[r] = st->prefix[r] | ((unsigned int)(D * t + j) << shift); new_rank[r] = (long long)(k - before); }
+            before += c[j];
         }
         __syncthreads();
     }
-    for (int i = t; i < 2 * kDigits; i += kSelThreads) (&st->hist[0][0])[i] = 0ull;
+    for (int i = t; i < 2 * kDigits; i += TPB) (&st->hist[0][0])[i] = 0ull;
     if (t < 2) {
         st->prefix[t] = new_prefix[t];
         st->rank[t] = new_rank[t];
@@ -81,15 +85,16 @@ __device__ __forceinline__ void select_scan(SelectState *st, float *out, int out
 }
 
 // PASS 0: digit = key[31:21];  PASS 1: key[20:10] among keys whose top 11 bits match;  PASS 2: key[9:0] among top-22 matches.
-// Pass 0 is a histogram of every element (unconditional shared red, as in collectors.cu).  In passes 1 and 2 only the elements of the
-// one or two buckets chosen so far count: a vector whose four keys all miss both prefixes -- the common case, the requested ranks sit
-// in the tails -- costs four masked compares and no shared-memory traffic, so these passes stream like the min/max collector.
-template <int PASS>
-__global__ void __launch_bounds__(kSelThreads, PASS == 0 ? 2 : 1)
+// Pass 0 is a histogram of every element (unconditional shared red, as in collectors.cu): two 1024-thread CTAs per SM, grid-stride.
+// In passes 1 and 2 only the elements of the one or two buckets chosen so far count: a vector whose four elements all miss both prefixes
+// -- the common case, the requested ranks sit in the tails -- costs one AND + three compares per element and no shared-memory traffic,
+// so these passes use the launch shape of the min/max collector: 256-thread CTAs, 8 per SM, every warp walking contiguous 2 KB segments.
+template <int PASS, int TPB>
+__global__ void __launch_bounds__(TPB, PASS == 0 ? 2 : 6)            // 32 / 40 registers; the scan of the last CTA may spill, it runs once
 select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restrict__ st, float *out, int out_stride) {
     __shared__ int sh[2][kDigits];
     __shared__ bool is_last;
-    for (int i = threadIdx.x; i < 2 * kDigits; i += kSelThreads) (&sh[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 2 * kDigits; i += TPB) (&sh[0][0])[i] = 0;
     __syncthreads();
     constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
     constexpr uint32_t dmask = PASS == 2 ? 0x3FFu : 0x7FFu;
@@ -113,18 +118,30 @@ select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restri
         if (PASS != 0 && !(hit(v.x) | hit(v.y) | hit(v.z) | hit(v.w))) return;
         count(order_key(v.x)); count(order_key(v.y)); count(order_key(v.z)); count(order_key(v.w));
     };
-    const int64_t first = (int64_t)blockIdx.x * kSelThreads + threadIdx.x, stride = (int64_t)gridDim.x * kSelThreads;
+    const int64_t first = (int64_t)blockIdx.x * TPB + threadIdx.x, stride = (int64_t)gridDim.x * TPB;
     if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
         const int64_t n4 = n >> 2;
         const float4 *x4 = reinterpret_cast<const float4 *>(x);
-        // passes 1-2 have no shared-memory traffic to overlap with: 8 loads in flight per thread instead of 4 (one 1024-thread CTA per SM)
-        constexpr int U = PASS == 0 ? 4 : 8;
-        for (int64_t i = first; i < n4; i += U * stride) {
-            float4 v[U];
+        constexpr int U = 4;
+        if (PASS == 0) {
+            for (int64_t i = first; i < n4; i += U * stride) {
+                float4 v[U];
 #pragma unroll
-            for (int j = 0; j < U; j++) if (i + j * stride < n4) v[j] = ld_stream4(x4 + i + j * stride);
+                for (int j = 0; j < U; j++) if (i + j * stride < n4) v[j] = ld_stream4(x4 + i + j * stride);
 #pragma unroll
-            for (int j = 0; j < U; j++) if (i + j * stride < n4) visit4(v[j]);
+                for (int j = 0; j < U; j++) if (i + j * stride < n4) visit4(v[j]);
+            }
+        } else {
+            // warp-contiguous segments of 32 lanes x U vectors (2 KB)
+            const int64_t lane = threadIdx.x & 31, warps = stride >> 5;
+            for (int64_t sg = first >> 5; sg * (32 * U) < n4; sg += warps) {
+                const int64_t base = sg * (32 * U) + lane;
+                float4 v[U];
+#pragma unroll
+                for (int j = 0; j < U; j++) if (base + j * 32 < n4) v[j] = ld_stream4(x4 + base + j * 32);
+#pragma unroll
+                for (int j = 0; j < U; j++) if (base + j * 32 < n4) visit4(v[j]);
+            }
         }
         const int64_t t = (n4 << 2) + first;
         if (t < n) count(order_key(x[t]));
@@ -132,7 +149,7 @@ select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restri
         for (int64_t i = first; i < n; i += stride) count(order_key(ld_stream1(x + i)));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kDigits; i += kSelThreads) {
+    for (int i = threadIdx.x; i < kDigits; i += TPB) {
         if (sh[0][i]) atomicAdd(&st->hist[0][i], (unsigned long long)sh[0][i]);
         if (!same && sh[1][i]) atomicAdd(&st->hist[1][i], (unsigned long long)sh[1][i]);
     }
@@ -143,22 +160,24 @@ select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restri
     __syncthreads();
     if (is_last) {
         __threadfence();
-        select_scan<PASS>(st, out, out_stride);
+        select_scan<PASS, TPB>(st, out, out_stride);
     }
 }
 
+constexpr int kFilterThreads = 256;
+
 static int select_two(const float *x, int64_t n, long long r0, long long r1, float *out, int out_stride, SelectState *st, cudaStream_t s) {
-    int64_t g = (n + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
-    if (g > kSMs) g = kSMs;
-    if (g < 1) g = 1;
-    select_init_kernel<<<1, 1024, 0, s>>>(st, r0, r1);
-    // pass 0 needs 32 registers per thread: two 1024-thread CTAs fit on an SM (passes 1-2 trade that for 8 loads in flight per thread)
+    // pass 0 needs 32 registers per thread: two 1024-thread CTAs fit on an SM
     int64_t g0 = (n + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
     if (g0 > 2 * kSMs) g0 = 2 * kSMs;
     if (g0 < 1) g0 = 1;
-    select_hist_kernel<0><<<(int)g0, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
-    select_hist_kernel<1><<<(int)g, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
-    select_hist_kernel<2><<<(int)g, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
+    int64_t g = (n + (int64_t)kFilterThreads * 16 - 1) / ((int64_t)kFilterThreads * 16);
+    if (g > 6 * kSMs) g = 6 * kSMs;                                       // 40 registers, 17.5 KB of smem: six CTAs per SM, one wave
+    if (g < 1) g = 1;
+    select_init_kernel<<<1, 1024, 0, s>>>(st, r0, r1);
+    select_hist_kernel<0, kSelThreads><<<(int)g0, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
+    select_hist_kernel<1, kFilterThreads><<<(int)g, kFilterThreads, 0, s>>>(x, n, st, out, out_stride);
+    select_hist_kernel<2, kFilterThreads><<<(int)g, kFilterThreads, 0, s>>>(x, n, st, out, out_stride);
     return (int)cudaGetLastError();
 }
 
