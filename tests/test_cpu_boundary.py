@@ -42,6 +42,38 @@ def test_c_abi_exports_every_declared_symbol(built):
     assert 'libtorch' not in deps and 'libpython' not in deps and 'libc10' not in deps
 
 
+def test_header_is_plain_c_and_a_c_program_links(built, tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and a C translation unit that only knows the header links against the
+    library and runs its host-side entry points (no GPU needed: version, error strings, argument validation, host MSE loss)."""
+    hdr = os.path.join(ROOT, 'include', 'ppq_b200.h')
+    assert subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-Werror', '-fsyntax-only', '-x', 'c', hdr]).returncode == 0
+    src = tmp_path / 'client.c'
+    src.write_text('''
+#include <stdio.h>
+#include <stdint.h>
+#include "ppq_b200.h"
+int main(void) {
+    int64_t hist[8] = {5, 4, 3, 2, 1, 0, 0, 7};
+    if (ppq_b200_abi_version() < 1) return 1;
+    /* null pointers / empty tensors are rejected before any launch */
+    if (ppq_b200_linear_quant_t(0, 0, 0, 0, 0, -128, 127, 0, 0) == 0) return 2;
+    if (ppq_b200_histogram_t(0, 16, 1.0f, 1, 0, 4096, 0) == 0) return 3;
+    printf("%s|%.9g\\n", ppq_b200_error_string(1), (double)ppq_b200_compute_mse_loss(hist, 8, 1, 2, 5));
+    return 0;
+}
+''')
+    exe = tmp_path / 'client'
+    cc = subprocess.run(['gcc', '-std=c99', '-Wall', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe),
+                         '-L', os.path.dirname(LIB), '-lppq_b200', '-Wl,-rpath,' + os.path.dirname(LIB)], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    msg, loss = run.stdout.strip().split('|')
+    assert 'invalid' in msg.lower()
+    from oracle import compute_mse_loss
+    assert np.float32(float(loss)) == np.float32(compute_mse_loss([5, 4, 3, 2, 1, 0, 0, 7], 1, 2, 5))
+
+
 def test_library_contains_sm100a_code_only(built):
     out = subprocess.run(['cuobjdump', '-lelf', LIB], capture_output=True, text=True).stdout
     archs = set(re.findall(r'sm_\d+a?', out))
