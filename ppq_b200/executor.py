@@ -273,6 +273,7 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
     from .calibration import ArenaCalibrator
     cfgs = executor.observed_configs()
     for c in cfgs: c.observer_algorithm = method
+    if iter(batches) is batches: batches = list(batches)                  # a one-shot iterator would leave phase 2 without data
     dev = next(executor.model.parameters()).device
     cal = ArenaCalibrator(len(cfgs), dev, method=method, group=group)
     static_in = None
