@@ -322,7 +322,7 @@ def test_fc_vs_oracle(ext, oracle):
 
 
 def test_ft_matches_hardware_fp8_away_from_ties(ext):
-    x = (torch.randn(1 << 20, device='cuda') * 10)
+    x = (torch.randn(1 << 20, device='cuda', generator=torch.Generator(device='cuda').manual_seed(325)) * 10)
     y = ext.QuantizeTensor_FT(x, t1(1.0), t1(0.0), 4, 3, -448.0, 448.0, 0)
     hw = x.to(torch.float8_e4m3fn).float()
     # differences are confined to exact ties (reference rule: ties toward zero; ~1e-6 of fp32 values are exact E4M3 ties)
@@ -398,7 +398,7 @@ def test_histogram_c_and_reference_histc_bar(ext, oracle):
         ext.Histogram_C(dev(x), axis, 0.02, True, h)
         assert np.array_equal(h.cpu().numpy(), oracle.histogram_c(x, axis, np.float32(0.02), 256, True)), shape
     # the reference's own check (tests/test_cuda_kernel.py:197-208): |kernel - torch.histc| < 100 on rand(128,3,224,224), 50 bins
-    t = torch.rand(16, 3, 224, 224, device='cuda')
+    t = torch.rand(16, 3, 224, 224, device='cuda', generator=torch.Generator(device='cuda').manual_seed(401))
     h = torch.zeros(50, dtype=torch.int32, device='cuda')
     ext.Histogram_T(t, 0.01, True, h)
     ref = torch.histc(torch.abs(t), bins=50, min=0, max=0.5)
@@ -532,7 +532,7 @@ def test_observers_end_to_end_vs_reference(ext, oracle):
 
 # ------------------------------------------------------------------------------------------------ raw C ABI + full-size properties
 def test_c_abi_direct_call(cabi, oracle):
-    x = torch.rand(1000003, device='cuda') * 32
+    x = torch.rand(1000003, device='cuda', generator=torch.Generator(device='cuda').manual_seed(535)) * 32
     y = torch.empty_like(x)
     s, o = t1(0.11), t1(17)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -548,14 +548,16 @@ def test_c_abi_direct_call(cabi, oracle):
 
 def test_full_size_properties(ext):
     """BASELINE-size tensors (1x2048x64x64 and BERT [32,512,768]): size-independent properties instead of a CPU oracle."""
+    g = torch.Generator(device='cuda').manual_seed(20260922)
     for shape in ((1, 2048, 64, 64), (32, 512, 768)):
-        x = torch.randn(shape, device='cuda') * 3
+        x = torch.randn(shape, device='cuda', generator=g) * 3
         s, o = t1(0.05), t1(0)
         y = ext.QuantizeTensor_LT(x, s, o, -128, 127, 0)
         assert torch.equal(ext.QuantizeTensor_LT(y, s, o, -128, 127, 0), y)                 # idempotent
         q = ext.QuantizeTensor_toInt(x, s, o, -128, 127, -1000, 0, 8)
         assert torch.equal(q.float() * 0.05, y)                                            # dequantised ints == fake-quant
-        assert (y - x).abs().max().item() <= max(0.025 + 1e-6, (x.abs().max().item() - 127 * 0.05))
+        # error bound: half a step inside the range, distance to the clamp outside it (+ fp32 rounding of the subtraction itself)
+        assert (y - x).abs().max().item() <= max(0.025, x.abs().max().item() - 127 * 0.05) + 1e-5
         assert torch.equal(ext.QuantizeTensor_LT(-x, s, o, -127, 127, 0), -ext.QuantizeTensor_LT(x, s, o, -127, 127, 0))  # odd symmetry
         # per-channel with equal scales == per-tensor
         C = shape[1]
