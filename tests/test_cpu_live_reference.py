@@ -138,3 +138,46 @@ def test_kl_and_mse_search_on_random_histograms(ref, oracle, seed):
             got = oracle.mse_search(hist, hs, ob._min, qmin, qmax, sym, loss_fn=oracle.mse_loss_python_twin)
             assert (np.float32(got[0]), float(got[1])) == (np.float32(want[0]), float(want[1])), (seed, it, sym)
     assert cfg.state == QuantizationStates.INITIAL
+
+
+def test_observers_end_to_end(ref, oracle, seed):
+    """ppq.lib.Observer (CPU path) on fresh data: min/max per tensor and per channel, percentile (kthvalue indices of the CPU branch), and the
+    two-phase KL / MSE observers, whose histogram (torch.histc on the CPU branch) is fed to the oracle's search."""
+    from ppq.lib import LinearQuantizationConfig, Observer
+    r = np.random.RandomState(seed + 3)
+    for it, algo in enumerate(('minmax', 'percentile', 'kl', 'mse', 'minmax', 'mse')):
+        sym = (it % 2 == 0) or algo == 'kl'
+        relu = bool(r.randint(2))
+        shape = (int(r.randint(1, 4)), int(r.randint(2, 9)), int(r.randint(5, 15)), int(r.randint(5, 15)))
+        data = [(np.maximum(x, 0) if relu else x) for x in ((r.standard_normal(shape) * 10 ** r.uniform(-1, 1)).astype(np.float32) for _ in range(3))]
+        qmin, qmax = (-128, 127) if sym else (0, 255)
+        cfg = LinearQuantizationConfig(symmetrical=sym, quant_min=qmin, quant_max=qmax, calibration=algo)
+        ob = Observer(cfg)
+        for x in data: ob.observe(torch.from_numpy(x))
+        ob.render_quantization_config()
+        lo = min(float(oracle.minmax_t(x)[0]) for x in data); hi = max(float(oracle.minmax_t(x)[1]) for x in data)
+        if algo in ('kl', 'mse'):
+            for x in data: ob.observe(torch.from_numpy(x))
+            hist, hs = ob._hist.numpy().copy(), float(ob._hist_scale)
+            assert (float(ob._min), float(ob._max)) == (lo, hi), (seed, it)
+            ob.render_quantization_config()
+            s, o = oracle.kl_search(hist, hs, 8) if algo == 'kl' else oracle.mse_search(hist, hs, lo, qmin, qmax, sym, loss_fn=oracle.mse_loss_python_twin)
+        elif algo == 'percentile':
+            pairs = []
+            for x in data:
+                v = np.sort(x.reshape(-1)); n = v.size
+                pairs.append([v[min(int(n * 0.9999), n - 1)], v[max(0, int(n * (1 - 0.9999)))]])
+            m = torch.tensor(np.array(pairs, np.float32)).mean(dim=0)
+            s, o = oracle.minmax_to_scale_offset(m[1].item(), m[0].item(), qmin, qmax, sym)
+        else:
+            s, o = oracle.minmax_to_scale_offset(lo, hi, qmin, qmax, sym)
+        assert (np.float32(s), np.float32(o)) == (np.float32(cfg.scale.item()), np.float32(cfg.offset.item())), (seed, it, algo, sym, relu, shape)
+    # per-channel symmetric min/max on a weight (ParameterQuantizePass path)
+    for axis in (0, 1):
+        w = (r.standard_normal((int(r.randint(2, 20)), int(r.randint(2, 20)), 3, 3)) * 0.1).astype(np.float32)
+        cfg = LinearQuantizationConfig(symmetrical=True, channel_axis=axis, calibration='minmax')
+        ob = Observer(cfg); ob.observe(torch.from_numpy(w)); ob.render_quantization_config()
+        lo, hi = oracle.minmax_c(w, axis)
+        so = [oracle.minmax_to_scale_offset(float(a), float(b), -128, 127, True) for a, b in zip(lo, hi)]
+        assert np.array_equal(np.float32([s for s, _ in so]), cfg.scale.numpy().reshape(-1)), (seed, axis)
+        assert np.array_equal(np.float32([o for _, o in so]), cfg.offset.numpy().reshape(-1)), (seed, axis)
