@@ -59,11 +59,19 @@ def test_install_routes_every_ffi_call_to_our_extension(ppq):
         with pytest.raises(RuntimeError, match='not on a CUDA device'):
             call()
     assert isinstance(ffi.CUDA.compute_mse_loss([1, 2, 3, 4], 0, 1, 2), float)
+    original = ppq_b200.install._saved['complie']
+    ppq_b200.install.uninstall()
+    assert type(ffi.CUDA_COMPLIER).complie is original and ffi.CUDA_COMPLIER.__CUDA_EXTENTION__ is not ext
 
 
 def test_observer_table_replaced(ppq):
     import ppq.quantization.observer as ref_obs
     import ppq_b200.install
     import ppq_b200.observer as ours
+    before = dict(ref_obs.OBSERVER_TABLE)
     ppq_b200.install.install(replace_observers=True)
-    assert ref_obs.OBSERVER_TABLE['minmax'] is ours.TorchMinMaxObserver and ref_obs.OBSERVER_TABLE['kl'] is ours.TorchHistObserver
+    try:
+        assert ref_obs.OBSERVER_TABLE['minmax'] is ours.TorchMinMaxObserver and ref_obs.OBSERVER_TABLE['kl'] is ours.TorchHistObserver
+    finally:
+        ppq_b200.install.uninstall()                      # leave the imported reference as found (other tests use its CPU path)
+    assert ref_obs.OBSERVER_TABLE == before
