@@ -1,0 +1,134 @@
+"""CPU twins of the three arithmetic shortcuts the sm_100a kernels take (ppq_b200/csrc/common.cuh, ops.cuh), checked here without a GPU:
+
+  1. ExactDiv: x / s through a hoisted reciprocal and two Markstein corrections == the IEEE fp32 quotient (exact rational arithmetic);
+  2. the "+ .5" rounding modes evaluated in fp32 (floor / ceil + fraction test) == the reference's double formulation (the oracle);
+  3. FloatOp<.., FAST>: clamp -> signed add of half-1 -> mask / magic-add sub-normal rounding == QuantizeScalarFloating (the oracle).
+
+The GPU parity tests prove the kernels; these prove the *algorithms*, so a change to either side shows up on the CPU suite first."""
+from fractions import Fraction
+
+import numpy as np
+
+F32_MIN_EXP = -149
+
+
+def rn32(fr: Fraction) -> np.float32:
+    """Correctly rounded (ties to even) float32 of an exact rational (single rounding, sub-normals included, no overflow expected)."""
+    if fr == 0: return np.float32(0.0)
+    sign = -1 if fr < 0 else 1
+    a = abs(fr)
+    e = a.numerator.bit_length() - a.denominator.bit_length()           # 2^(e-1) <= a < 2^(e+1)
+    if a < Fraction(2) ** e: e -= 1                                       # now 2^e <= a < 2^(e+1)
+    ulp_exp = max(e - 23, F32_MIN_EXP)
+    m = a / (Fraction(2) ** ulp_exp)
+    n = m.numerator // m.denominator
+    rem = m - n
+    if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and (n & 1)): n += 1
+    return np.float32(sign * float(n) * 2.0 ** ulp_exp)                  # n < 2^25 and the power of two are exact in double -> exact product
+
+
+def fr(x) -> Fraction:
+    return Fraction(float(x))
+
+
+def fma32(a, b, c) -> np.float32:
+    return rn32(fr(a) * fr(b) + fr(c))
+
+
+def markstein(x: np.float32, s: np.float32) -> np.float32:
+    r = np.float32(1.0) / s                                               # == __frcp_rn(s): IEEE division is correctly rounded
+    q0 = rn32(fr(x) * fr(r))
+    e0 = fma32(-q0, s, x)
+    q1 = fma32(e0, r, q0)
+    e1 = fma32(-q1, s, x)
+    return fma32(e1, r, q1)
+
+
+def test_markstein_division_is_the_ieee_quotient():
+    r = np.random.RandomState(2026)
+    n_checked = 0
+    with np.errstate(all='ignore'):
+        for it in range(6000):
+            s = np.float32(r.uniform(1, 2) * 2.0 ** r.randint(-59, 60) * (1 if r.rand() < 0.9 else -1))
+            kind = it % 4
+            if kind == 0: x = np.float32(r.standard_normal() * 10.0 ** r.uniform(-6, 6))
+            elif kind == 1: x = np.float32((r.randint(-300, 300) + 0.5)) * s                     # quotient next to a rounding tie
+            elif kind == 2: x = np.nextafter(np.float32((r.randint(-300, 300) + 0.5)) * s, np.float32(r.choice([-np.inf, np.inf])))
+            else: x = np.float32(r.randint(-2 ** 24, 2 ** 24)) * np.float32(2.0 ** r.randint(-20, 20))
+            want = x / s
+            if not np.isfinite(want) or abs(float(want)) >= 2.0 ** 31 or (want != 0 and abs(float(want)) < 2.0 ** -40): continue    # slow-path domain
+            if abs(float(x)) < 2.0 ** -100 and x != 0: continue                                    # residuals could underflow: harmless, see common.cuh
+            got = markstein(np.float32(x), s)
+            assert got.view(np.uint32) == np.float32(want).view(np.uint32) or (got == 0 and want == 0), (it, float(x), float(s), float(got), float(want))
+            n_checked += 1
+    assert n_checked > 4000
+
+
+def sat_i32(a):
+    a = np.where(np.isnan(a), 0.0, a.astype(np.float64))
+    return np.clip(a, -2.0 ** 31, 2.0 ** 31 - 1).astype(np.int64)
+
+
+def dev_half_up(v):   return sat_i32(np.floor(v)) + ((v - np.floor(v)).astype(np.float32) >= np.float32(0.5))
+def dev_half_down(v): return sat_i32(np.ceil(v)) - ((np.ceil(v) - v).astype(np.float32) >= np.float32(0.5))
+
+
+def dev_round(v, mode):
+    if mode == 1: return dev_half_up(v)
+    if mode == 2: return dev_half_down(v)
+    if mode == 3: return np.where(v > 0, dev_half_down(v), dev_half_up(v))
+    return np.where(v > 0, dev_half_up(v), dev_half_down(v))               # 4 (far from zero) and 5 (round()): the same function
+
+
+def test_fp32_rounding_formulation_equals_the_double_one(oracle):
+    r = np.random.RandomState(7)
+    h = np.arange(-3000, 3000, dtype=np.float32) + np.float32(0.5)
+    tiny = np.float32([-1e-30, 1e-30, -1e-45, 1e-45, -0.49999997, 0.49999997, -0.50000006, 0.50000006, -0.5, 0.5, -0.0, 0.0,
+                       -(0.5 - 2.0 ** -25), 0.5 - 2.0 ** -25, -0.99999994, 0.99999994, -1.0000001, 1.0000001, -0.25 - 2.0 ** -26])
+    big = np.float32([2 ** 23 - 0.5, 2 ** 23 + 1, 2 ** 22 + 0.5, -(2 ** 22 + 0.5), -(2 ** 23 - 0.5), 2 ** 24 + 2, 2147483520.0, -2147483520.0,
+                      2 ** 31, -2 ** 31, -2147483904.0, 3e38, -3e38, np.inf, -np.inf, np.nan, 4194303.5, -4194303.5, 8388607.5, -8388607.5])
+    rnd = (r.standard_normal(400000) * np.exp(r.uniform(-25, 25, 400000))).astype(np.float32)
+    x = np.concatenate([h, np.nextafter(h, np.float32(np.inf)), np.nextafter(h, np.float32(-np.inf)), tiny, big, rnd, -rnd])
+    with np.errstate(all='ignore'):
+        for mode in (1, 2, 3, 4, 5):
+            want = oracle.linear_quant_t(x, np.float32(1.0), 0, -2 ** 31, 2 ** 31 - 1, mode, return_int=True)[1].astype(np.int64)
+            got = dev_round(x, mode)
+            bad = np.flatnonzero(want != got)
+            assert bad.size == 0, (mode, x[bad[:4]], want[bad[:4]], got[bad[:4]])
+
+
+def fp_fast_twin(x, s, E, M, cmin, cmax):
+    """FloatOp<HALF_EVEN, FAST>::grid + dequant with offset 0 in numpy: bit for bit what ops.cuh does."""
+    u = (x / np.float32(s)).astype(np.float32)
+    emin, emax = -(1 << (E - 1)) + 1, 1 << (E - 1)
+    top = (~(0x007FFFFF >> M)) & 0x007FFFFF
+    tmax = np.array([((emax + 127) << 23) + top], np.uint32).view(np.float32)[0]
+    hi, lo = np.float32(min(cmax, tmax)), np.float32(max(cmin, -tmax))
+    k = (1 << (E - 1)) + M - 2
+    magic = np.array([((127 + 23 - k) << 23) | 0x00400000], np.uint32).view(np.float32)[0]
+    thresh = np.array([(emin + 1 + 127) << 23], np.uint32).view(np.float32)[0]
+    half_minus1, keep = np.uint32((1 << (22 - M)) - 1), np.uint32((~((1 << (23 - M)) - 1)) & 0xFFFFFFFF)
+    nan = np.isnan(u)
+    uc = np.minimum(np.maximum(u, lo), hi)
+    uc_bits = np.where(nan, np.uint32(0x7FFFFFFF), uc.view(np.uint32))    # min.NaN / max.NaN return the canonical NaN
+    nb = ((uc_bits.astype(np.uint64) + half_minus1) & 0xFFFFFFFF).astype(np.uint32) & keep
+    sub = ((uc + magic).astype(np.float32) - magic).astype(np.float32)
+    q = np.where(np.abs(uc) < thresh, sub, nb.view(np.float32))
+    q = np.where(nan, nb.view(np.float32), q)
+    return (q * np.float32(s)).astype(np.float32)
+
+
+def test_fp8_fast_path_twin_equals_the_reference_algorithm(oracle):
+    r = np.random.RandomState(11)
+    x = (r.standard_normal(300000) * np.exp(r.uniform(-12, 8, 300000))).astype(np.float32)
+    x[::3] = x[::3].astype(np.float16).astype(np.float32)                  # tie-rich
+    sp = np.float32([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, 464.0, 480.0, 448.0, 1.1875, 1.4375, 2.375, 19.0, -1.1875, 1.5 * 2 ** -9,
+                     2.5 * 2 ** -9, 2 ** -10, -2 ** -11, 2 ** -6, 2 ** -6 * (1 - 2 ** -24), 3e38, -3e38, 57344.0, 61440.0, 65504.0])
+    x[:sp.size] = sp
+    with np.errstate(all='ignore'):
+        for (E, M, cmin, cmax) in ((4, 3, -448.0, 448.0), (5, 2, -57344.0, 57344.0), (4, 3, -240.0, 240.0), (5, 10, -65504.0, 65504.0), (3, 4, -30.0, 30.0)):
+            for s in (1.0, 0.125, 4.0, 0.3):
+                want = oracle.float_quant_t(x, np.float32(s), 0.0, E, M, cmin, cmax, 0)
+                got = fp_fast_twin(x, s, E, M, cmin, cmax)
+                bad = np.flatnonzero(got.view(np.uint32) != want.view(np.uint32))
+                assert bad.size == 0, (E, M, s, x[bad[:4]], got[bad[:4]], want[bad[:4]])
