@@ -132,3 +132,26 @@ def test_fp8_fast_path_twin_equals_the_reference_algorithm(oracle):
                 got = fp_fast_twin(x, s, E, M, cmin, cmax)
                 bad = np.flatnonzero(got.view(np.uint32) != want.view(np.uint32))
                 assert bad.size == 0, (E, M, s, x[bad[:4]], got[bad[:4]], want[bad[:4]])
+
+
+def test_radix_select_raw_prefix_filter_has_no_false_negatives():
+    """select.cu passes 1-2 reject elements on the raw bits before computing the order-preserving key.  Twin of order_key / raw_of / hit:
+    every element whose key matches a chosen prefix must pass the filter (false positives are allowed: the exact test follows)."""
+    r = np.random.RandomState(5)
+    b = r.randint(0, 2 ** 32, size=400000, dtype=np.uint64).astype(np.uint32)
+    b[:8] = np.uint32([0x00000000, 0x80000000, 0x7F800000, 0xFF800000, 0x7FC00000, 0xFFC00000, 0x00000001, 0x80000001])
+    bz = np.where(b == 0x80000000, np.uint32(0), b)                       # -0.0 shares +0.0's key
+    key = np.where(bz & 0x80000000, ~bz, bz | np.uint32(0x80000000)).astype(np.uint32)
+    for pmask in (np.uint32(0xFFE00000), np.uint32(0xFFFFFC00)):
+        prefixes = [np.uint32(0x80000000), np.uint32(0x7FFFFFFF) & pmask,      # the bucket of +0 (takes -0.0 too) and the bucket just below it
+                    key[17] & pmask, key[99] & pmask, key[12345] & pmask, key[5] & pmask, key[1] & pmask]
+        for p0 in prefixes:
+            for p1 in (prefixes[0], prefixes[2], p0):
+                def raw_of(p): return (p & np.uint32(0x7FFFFFFF)) if (p & 0x80000000) else (~p & pmask)
+                c0, c1 = raw_of(p0), raw_of(p1)
+                c2 = np.uint32(0x80000000) if (p0 == 0x80000000 or p1 == 0x80000000) else c0
+                t = b & pmask
+                hit = (t == c0) | (t == c1) | (t == c2)
+                exact = ((key & pmask) == p0) | ((key & pmask) == p1)
+                assert not np.any(exact & ~hit), (hex(int(pmask)), hex(int(p0)), hex(int(p1)))
+                assert (hit & ~exact).sum() <= 2 + (b == 0x80000000).sum() + ((b & pmask) == 0x80000000).sum()      # only the -0.0 pattern's bucket
