@@ -155,3 +155,38 @@ def test_radix_select_raw_prefix_filter_has_no_false_negatives():
                 exact = ((key & pmask) == p0) | ((key & pmask) == p1)
                 assert not np.any(exact & ~hit), (hex(int(pmask)), hex(int(p0)), hex(int(p1)))
                 assert (hit & ~exact).sum() <= 2 + (b == 0x80000000).sum() + ((b & pmask) == 0x80000000).sum()      # only the -0.0 pattern's bucket
+
+
+def test_raw_bit_float_atomics_give_min_and_max_for_mixed_signs():
+    """common.cuh atomic_{max,min}_float: non-negative patterns go through a signed-int atomic, negative ones through an unsigned atomic
+    of the opposite sense; the slot starts at -inf / +inf; NaN is injected as +NaN (max slot) / -NaN (min slot) and must win.  Twin on
+    Python ints, any arrival order."""
+    def as_int(u): return u - (1 << 32) if u & 0x80000000 else u
+    def atomic_max_float(slot, u):          # slot, u: raw uint32 patterns
+        if not (u >> 31): return max(as_int(slot), as_int(u)) & 0xFFFFFFFF        # atomicMax(int*)
+        return min(slot, u)                                                      # atomicMin(unsigned*)
+    def atomic_min_float(slot, u):
+        if not (u >> 31): return min(as_int(slot), as_int(u)) & 0xFFFFFFFF        # atomicMin(int*)
+        return max(slot, u)                                                      # atomicMax(unsigned*)
+    r = np.random.RandomState(3)
+    for it in range(300):
+        n = int(r.randint(1, 40))
+        kind = it % 5
+        v = (r.standard_normal(n) * 10.0 ** r.uniform(-3, 3)).astype(np.float32)
+        if kind == 1: v = np.abs(v)
+        if kind == 2: v = -np.abs(v)
+        if kind == 3: v[r.randint(n)] = np.float32(-0.0); v[r.randint(n)] = np.float32(0.0)
+        if kind == 4: v[:] = np.float32(r.choice([-0.0, 0.0, np.inf, -np.inf, 1e-45, -1e-45]))
+        hi, lo = 0xFF800000, 0x7F800000                                          # minmax_init_kernel: max = -inf, min = +inf
+        for u in v.view(np.uint32).tolist():
+            hi, lo = atomic_max_float(hi, u), atomic_min_float(lo, u)
+        got_hi, got_lo = np.array([hi], np.uint32).view(np.float32)[0], np.array([lo], np.uint32).view(np.float32)[0]
+        assert got_hi == v.max() and got_lo == v.min(), (it, v, got_lo, got_hi)   # value equality (either zero may represent 0)
+        # NaN poisoning: whatever came before or comes after, the slot ends up NaN
+        order = r.permutation(n + 1)
+        hi, lo = 0xFF800000, 0x7F800000
+        for j in order:
+            if j == n: hi, lo = atomic_max_float(hi, 0x7FC00000), atomic_min_float(lo, 0xFFC00000)
+            else:
+                u = int(v.view(np.uint32)[j]); hi, lo = atomic_max_float(hi, u), atomic_min_float(lo, u)
+        assert hi == 0x7FC00000 and lo == 0xFFC00000, (it, hex(hi), hex(lo))
