@@ -190,3 +190,30 @@ def test_raw_bit_float_atomics_give_min_and_max_for_mixed_signs():
             else:
                 u = int(v.view(np.uint32)[j]); hi, lo = atomic_max_float(hi, u), atomic_min_float(lo, u)
         assert hi == 0x7FC00000 and lo == 0xFFC00000, (it, hex(hi), hex(lo))
+
+
+def test_histogram_slot_arithmetic_twin(oracle):
+    """collectors.cu SymBin / AsymBin: slot = saturating floor of the fp32 quotient, then ONE unsigned min against `bins` (clip: everything
+    out of range, negative wrap-around included, lands in the trash slot) or a clamp to the last bin (no clip) -- against the oracle's
+    restatement of the reference's branches (sort.cu:75-89, 113-139)."""
+    r = np.random.RandomState(13)
+    x = (r.standard_normal(200000) * np.exp(r.uniform(-3, 3, 200000))).astype(np.float32)
+    x[:10] = np.float32([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 3e38, -3e38, 1.0])
+    with np.errstate(all='ignore'):
+        def floor_sat(t):
+            t = np.where(np.isnan(t), 0.0, np.floor(t.astype(np.float64)))
+            return np.clip(t, -2.0 ** 31, 2.0 ** 31 - 1).astype(np.int64)
+        for bins in (50, 2048, 4096):
+            for hs in (np.float32(0.001), np.float32(0.37), np.float32(x[np.isfinite(x)].max() / bins)):
+                for clip in (True, False):
+                    b = floor_sat((np.abs(x) / hs).astype(np.float32))
+                    slot = np.minimum(b & 0xFFFFFFFF, bins) if clip else np.minimum(b, bins - 1)
+                    got = np.bincount(slot[slot < bins], minlength=bins).astype(np.int32)
+                    assert np.array_equal(got, oracle.histogram_t(x, hs, bins, clip)), ('sym', bins, float(hs), clip)
+            for (vmin, vmax) in ((np.float32(-2.5), np.float32(3.0)), (np.float32(0.0), np.float32(10.0))):
+                for clip in (True, False):
+                    hs = ((vmax - vmin) / np.float32(bins)).astype(np.float32)                       # fp32, like the kernel
+                    b = floor_sat(((x - vmin).astype(np.float32) / hs).astype(np.float32))
+                    slot = np.minimum(b & 0xFFFFFFFF, bins) if clip else np.maximum(np.minimum(b, bins - 1), 0)
+                    got = np.bincount(slot[slot < bins], minlength=bins).astype(np.int32)
+                    assert np.array_equal(got, oracle.histogram_asym_t(x, vmin, vmax, bins, clip)), ('asym', bins, float(vmin), float(vmax), clip)
