@@ -217,3 +217,57 @@ def test_histogram_slot_arithmetic_twin(oracle):
                     slot = np.minimum(b & 0xFFFFFFFF, bins) if clip else np.maximum(np.minimum(b, bins - 1), 0)
                     got = np.bincount(slot[slot < bins], minlength=bins).astype(np.int32)
                     assert np.array_equal(got, oracle.histogram_asym_t(x, vmin, vmax, bins, clip)), ('asym', bins, float(vmin), float(vmax), clip)
+
+
+def test_multi_tensor_span_partitions_cover_every_element_exactly_once():
+    """Index twins of the two multi-tensor kernels: (1) multi_histogram_t_kernel / multi_minmax (collectors.cu) give each CTA a contiguous
+    span of the concatenated tensors and round the cut points inside a tensor up to a multiple of 4 elements on BOTH sides; (2)
+    multi_channel_kernel (fakequant.cu) splits the concatenation of 512-element warp segments.  Every element of every tensor must be
+    visited exactly once, whatever the sizes."""
+    r = np.random.RandomState(17)
+    for it in range(200):
+        T = int(r.randint(1, 12))
+        ns = [int(r.choice([1, 2, 3, 5, 511, 512, 513, 4096, 70001, int(r.randint(1, 200000))])) for _ in range(T)]
+        grid = int(r.choice([1, 2, 7, 148, 1184]))
+        # ---- (1) element spans
+        prefix = np.concatenate([[0], np.cumsum(ns)])
+        total = int(prefix[-1])
+        span = -(-total // grid); span = (span + 3) & ~3
+        seen = [np.zeros(n, np.int32) for n in ns]
+        for cta in range(grid):
+            s0 = cta * span; s1 = min(s0 + span, total)
+            if s0 >= total: continue
+            t = int(np.searchsorted(prefix, s0, side='right') - 1); t = min(t, T - 1)
+            while t < T and prefix[t] < s1:
+                n = ns[t]
+                a = max(s0 - int(prefix[t]), 0); b = min(s1 - int(prefix[t]), n)
+                a = min((a + 3) & ~3, n)
+                if b < n: b = (b + 3) & ~3
+                b = min(b, n)
+                if b > a: seen[t][a:b] += 1
+                t += 1
+        assert all((s == 1).all() for s in seen), (it, ns, grid)
+        # ---- (2) segment spans, 8 warps per CTA, 32 lanes x 4 vectors (or groups) of 4 elements per segment
+        segs = [(-(-n // 512)) if n > 0 else 0 for n in ns]
+        sp = np.concatenate([[0], np.cumsum(segs)]); tot = int(sp[-1])
+        span = -(-tot // grid)
+        seen = [np.zeros(n, np.int32) for n in ns]
+        for cta in range(grid):
+            s0 = cta * span; s1 = min(s0 + span, tot)
+            if s0 >= tot: continue
+            t = int(np.searchsorted(sp, s0, side='right') - 1); t = min(t, T - 1)
+            while t < T and sp[t] < s1:
+                first, nseg = int(sp[t]), segs[t]
+                if nseg:
+                    a = max(s0 - first, 0); b = min(s1 - first, nseg)
+                    n = ns[t]
+                    for warp in range(8):
+                        for sg in range(a + warp, b, 8):
+                            g = sg * 128 + np.arange(128)                          # the 32 x 4 vector / group indices of this segment
+                            e0 = g * 4
+                            for k in range(4):
+                                idx = e0 + k
+                                idx = idx[idx < n]
+                                seen[t][idx] += 1
+                t += 1
+        assert all((s == 1).all() for s in seen), (it, ns, grid)
