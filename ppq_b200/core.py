@@ -88,7 +88,8 @@ def set_state(config, name: str) -> None:
 
 
 class TensorQuantizationConfig:
-    """The parameter block of every quantization call (ppq/core/quant.py:367-896, ctor :518-599)."""
+    """The parameter block of every quantization call (ppq/core/quant.py:367-896, ctor :518-599), including the union-find
+    `dominated_by` / `master_by` links (:646-712): a dominated config reads scale / offset from the root of its group."""
 
     def __init__(self, policy: QuantizationPolicy, rounding: RoundingPolicy = RoundingPolicy.ROUND_HALF_EVEN,
                  num_of_bits: int = 8, quant_min=-127, quant_max=128, exponent_bits: int = 0,
@@ -101,17 +102,85 @@ class TensorQuantizationConfig:
         self.quant_min = quant_min
         self.quant_max = quant_max
         self.exponent_bits = exponent_bits
-        self.scale = scale
-        self.offset = offset
+        self._scale = scale
+        self._offset = offset
         self.observer_algorithm = observer_algorithm
         self.detail = {} if detail is None else detail
         self.channel_axis = channel_axis
         self.state = state
+        self._dominator = self
 
     @property
     def mantissa_bits(self) -> int:
         # ppq/core/quant.py:793-800
         return self.num_of_bits - self.exponent_bits - 1
+
+    def is_same_scheme(self, o: 'TensorQuantizationConfig') -> bool:
+        """quant.py:632-644."""
+        return (self.quant_max == o.quant_max and self.quant_min == o.quant_min and self.policy == o.policy and
+                self.num_of_bits == o.num_of_bits and self.exponent_bits == o.exponent_bits and
+                self.channel_axis == o.channel_axis and self.rounding == o.rounding)
+
+    # -- union-find over quantization groups (quant.py:646-712)
+    @property
+    def dominated_by(self) -> 'TensorQuantizationConfig':
+        if self._dominator is self: return self
+        root = self._dominator.dominated_by
+        self._dominator = root                                      # path compression, as upstream
+        return root
+
+    @dominated_by.setter
+    def dominated_by(self, o: 'TensorQuantizationConfig'):
+        assert isinstance(o, TensorQuantizationConfig), 'Can only set this attribute with another tensor config.'
+        if o is self: raise ValueError('Error with TQC.dominated_by = o: o must not equal to TQC its self.')
+        root, dominator = self.dominated_by, o.dominated_by
+        if self is dominator:
+            raise ValueError('Can not Assign Dominator like this, Circular reference was detected. Son TQC can not dominate its Father.')
+        if dominator is not root:
+            root._dominator = dominator
+            self._dominator = dominator
+            root.state = QuantizationStates.OVERLAPPED
+            self.state = QuantizationStates.OVERLAPPED
+
+    @property
+    def master_by(self) -> 'TensorQuantizationConfig':
+        return self.dominated_by
+
+    @master_by.setter
+    def master_by(self, master: 'TensorQuantizationConfig'):
+        if not isinstance(master, TensorQuantizationConfig):
+            raise TypeError(f'Error with TQC.master_by(o): o must be another Tensor Quantization Config, however {type(master)} was given.')
+        if master is self: raise ValueError('Error with TQC.dominated_by = o: o must not equal to TQC its self.')
+        self._dominator = master
+        self.state = QuantizationStates.PASSIVE if (master.scale is not None and master.offset is not None) else QuantizationStates.PASSIVE_INIT
+
+    def is_revisable(self) -> bool:
+        return self.dominated_by is self and self.state in {QuantizationStates.ACTIVATED, QuantizationStates.FP32, QuantizationStates.INITIAL,
+                                                           QuantizationStates.PASSIVE, QuantizationStates.PASSIVE_INIT}
+
+    @property
+    def scale(self) -> Optional[torch.Tensor]:
+        return self._scale if self.dominated_by is self else self.dominated_by.scale
+
+    @scale.setter
+    def scale(self, value):
+        if not self.is_revisable():
+            raise PermissionError('Can not change scale of this tensor quantization configuration now. '
+                                  'It has been overlapped or has an inactive state. '
+                                  'Due to it is not a active config, any change of this configuration is not allowed.')
+        self._scale = value
+
+    @property
+    def offset(self) -> Optional[torch.Tensor]:
+        return self._offset if self.dominated_by is self else self.dominated_by.offset
+
+    @offset.setter
+    def offset(self, value):
+        if not self.is_revisable():
+            raise PermissionError('Can not change offset of this tensor quantization configuration now. '
+                                  'It has been overlapped or has an inactive state. '
+                                  'Due to it is not a active config, any change of this configuration is not allowed.')
+        self._offset = value
 
 
 def LinearQuantizationConfig(symmetrical: bool = True, dynamic: bool = False, power_of_2: bool = False,

@@ -1,17 +1,29 @@
 """Executor: the slice of TorchExecutor that the hot path lives in (/root/reference/ppq/executor/torch.py:457-577, 610-652)
 for a torch.nn.Module network -- no graph IR, no ONNX (neither is part of the path).
 
-What is mirrored, with the reference's semantics:
-  * every quantable operation (a Conv2d / Linear / ReLU / pooling call site) owns TensorQuantizationConfigs for its inputs,
-    parameters and outputs with the TensorRT-INT8 policy of ppq/quantization/quantizer/TensorRTQuantizer.py:12-105:
-    per-tensor symmetric INT8 activations, per-channel symmetric INT8 weights on axis 0 ('minmax'), bias FP32;
+What is mirrored, with the reference's semantics (pinned against the unmodified reference pipeline on a programmatically built
+BaseGraph: tests/golden/graph_pipeline.npz, tests/test_cpu_graph_parity.py, tests/test_gpu_graph_parity.py):
+  * every quantable operation (a call site of a Conv2d / Linear / ReLU / pooling / Add / Flatten ... module) owns one
+    TensorQuantizationConfig per tensor input, one for its weight and one for its output, with the TensorRT-INT8 policy of
+    ppq/quantization/quantizer/TensorRTQuantizer.py:12-105: per-tensor symmetric INT8 activations ('percentile' by default),
+    per-channel symmetric INT8 weights on axis 0 ('minmax'), bias FP32;
+  * the topology passes that decide WHICH tensors are observed and quantised, in the reference's order
+    (quantizer/base.py:249-350):  QuantizeFusionPass (optim/refine.py:91-306: computing op -> activation, passive operations,
+    anything -> Relu/Clip) then QuantizeSimplifyPass (refine.py:17-88: an input config whose tensor was already quantised by the
+    producer's output config with the same scheme is OVERLAPPED), on the union-find `dominated_by` links of the configs;
   * forward(inputs, hooks): for each operation call quantize_function on every input and parameter (weights are re-quantised
     on EVERY forward until baked: torch.py:516-518), run pre-forward hooks with (fp32, quantised) values, run the op, quantise
     the outputs, run post-forward hooks (torch.py:526-553).  Only ACTIVATED / PASSIVE configs quantise (core/quant.py:357-359);
-  * Conv -> ReLU fusion marks the conv output OVERLAPPED (QuantizeFusionPass) so it is neither observed nor
-    quantised; downstream inputs are dominated by the producer's output config;
-  * dummy_forward-style ParameterQuantizePass (optim/parameters.py:172-215): per-channel min/max + scale search for weights.
+  * ParameterQuantizePass (optim/parameters.py:172-215), QuantAlignmentPass for element-wise ops (refine.py:309-546, 'Align to
+    Large' + force_overlap, the default setting: api/setting.py:251-256) and ParameterBakingPass (optim/baking.py:34-47,
+    IR/quantize.py:98-111).
 Conv / Gemm execution itself stays in torch (cuDNN / cuBLAS), as in the reference.
+
+Functional calls inside a network (`out += identity`, torch.flatten) are invisible to module hooks.  A tensor that reaches an
+operation without a visible producer gets its own INITIAL input config (what the reference does for an input coming from a
+non-quantable operation), except: a view of a known tensor shares its producer's config (Reshape / Flatten / Transpose are
+passive operations upstream), and a Relu / Clip fed by an invisible operation fuses with it (refine.py:293-306).  Use the
+`Add` / `Concat` modules of this file when element-wise ops must be quantised and aligned like the reference's graph.
 
 B200-native addition: `collect=True` makes the executor hand the observed fp32 tensors of a whole forward to an ArenaCalibrator
 (one multi-tensor launch per phase) instead of firing one observer launch per tensor.
@@ -23,8 +35,33 @@ import torch
 from .core import LinearQuantizationConfig, QuantizationStates, TensorQuantizationConfig
 from .qfunction import PPQuantFunction
 
-_KINDS = {torch.nn.Conv2d: 'Conv', torch.nn.Linear: 'Gemm', torch.nn.ReLU: 'Relu', torch.nn.ReLU6: 'Clip',
-          torch.nn.MaxPool2d: 'MaxPool', torch.nn.AdaptiveAvgPool2d: 'GlobalAveragePool', torch.nn.AvgPool2d: 'AveragePool'}
+
+class Add(torch.nn.Module):
+    """Element-wise sum as a module, so that the executor sees it as the reference sees an ONNX `Add`."""
+
+    def forward(self, a, b):
+        return a + b
+
+
+class Concat(torch.nn.Module):
+    def __init__(self, dim: int = 1):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, *tensors):
+        return torch.cat(tensors, dim=self.dim)
+
+
+_KINDS = {torch.nn.Conv2d: 'Conv', torch.nn.ConvTranspose2d: 'ConvTranspose', torch.nn.Linear: 'Gemm', torch.nn.ReLU: 'Relu',
+          torch.nn.ReLU6: 'Clip', torch.nn.MaxPool2d: 'MaxPool', torch.nn.AdaptiveAvgPool2d: 'GlobalAveragePool',
+          torch.nn.AvgPool2d: 'AveragePool', torch.nn.Flatten: 'Flatten', torch.nn.Sigmoid: 'Sigmoid', torch.nn.GELU: 'Gelu',
+          torch.nn.Hardswish: 'HardSwish', torch.nn.Softmax: 'Softmax', torch.nn.LeakyReLU: 'LeakyRelu', Add: 'Add', Concat: 'Concat'}
+COMPUTING_OP = {'Conv', 'Gemm', 'ConvTranspose', 'MatMul'}                              # core/common.py:55
+# core/common.py:51-53 -- as written upstream, where a missing comma makes 'Dropout' 'Slice' one string: neither is passive
+PASSIVE_OPERATIONS = {'MaxPool', 'GlobalMaxPool', 'Reshape', 'Flatten', 'Identity', 'DropoutSlice', 'Pad', 'Split', 'Transpose',
+                      'Interp', 'Squeeze', 'Unsqueeze'}
+ACTIVATION_FUSION_TYPES = {'Relu', 'Clip', 'Swish', 'SoftPlus', 'Sigmoid', 'Gelu'}     # TensorRTQuantizer.py:103-104
+ELEMENTWISE_ALIGNMENT_TYPES = {'Add', 'Sub', 'Sum'}                                     # core/common.py:60-63
 
 
 def fuse_conv_bn(model: torch.nn.Module) -> torch.nn.Module:
@@ -48,19 +85,27 @@ def fuse_conv_bn(model: torch.nn.Module) -> torch.nn.Module:
 
 class QuantableOperation:
     """One call site of a quantable module.  `input_configs()` / `output_configs()` are what OperationObserver walks
-    (observer/__init__.py:92-113)."""
+    (observer/__init__.py:92-113).  `sources[i]` is the operation that produced tensor input i (None: graph input or invisible)."""
 
-    def __init__(self, name: str, module: torch.nn.Module, kind: str, is_graph_input: bool):
+    def __init__(self, name: str, module: torch.nn.Module, kind: str, num_inputs: int):
         self.name, self.module, self.kind = name, module, kind
         act = dict(symmetrical=True, quant_min=-128, quant_max=127, calibration='percentile')
-        self.input_cfg: Optional[TensorQuantizationConfig] = LinearQuantizationConfig(**act) if is_graph_input else None
+        self.input_cfgs: List[TensorQuantizationConfig] = [LinearQuantizationConfig(**act) for _ in range(num_inputs)]
+        self.sources: List[Optional['QuantableOperation']] = [None] * num_inputs
+        self.invisible_source: List[bool] = [False] * num_inputs       # the tensor was modified in place after its producer ran
         self.weight_cfg: Optional[TensorQuantizationConfig] = None
-        if kind in ('Conv', 'Gemm'):
-            self.weight_cfg = LinearQuantizationConfig(symmetrical=True, quant_min=-128, quant_max=127, channel_axis=0, calibration='minmax')
+        if kind in ('Conv', 'Gemm', 'ConvTranspose'):
+            self.weight_cfg = LinearQuantizationConfig(symmetrical=True, quant_min=-128, quant_max=127, calibration='minmax',
+                                                       channel_axis=1 if kind == 'ConvTranspose' else 0)
         self.output_cfg: TensorQuantizationConfig = LinearQuantizationConfig(**act)
+        self.consumers: List[tuple] = []                               # (operation, input index)
+
+    @property
+    def input_cfg(self) -> Optional[TensorQuantizationConfig]:
+        return self.input_cfgs[0] if self.input_cfgs else None
 
     def input_configs(self):
-        if self.input_cfg is not None: yield (self.name + ':in', self.input_cfg, False)
+        for i, c in enumerate(self.input_cfgs): yield (f'{self.name}:in{i}', c, False)
         if self.weight_cfg is not None: yield (self.name + ':weight', self.weight_cfg, True)
 
     def output_configs(self):
@@ -75,7 +120,8 @@ class TorchExecutor:
         self._calls: Dict[int, int] = {}
         self._names = {id(m): n for n, m in self.model.named_modules()}
         self._hooks, self._collect, self._collected, self._sink = None, False, None, None
-        self._tracing, self._last_out, self._wq = True, None, {}
+        self._tracing, self._wq, self._swapped = True, {}, {}
+        self._produced = {}                                            # id(tensor) -> (operation, tensor, version at production)
         self._quant_fn = PPQuantFunction
         for m in self.model.modules():
             if type(m) in _KINDS:
@@ -85,6 +131,9 @@ class TorchExecutor:
             self._begin()
             self.model(example_input)
         self._tracing = False
+        self._produced = {}
+        self._fusion_pass()
+        self._simplify_pass()
 
     # -- graph view used by the calibration pass
     def quantable_operations(self):
@@ -95,10 +144,51 @@ class TorchExecutor:
         if config is None or not QuantizationStates.is_activated(config.state): return tensor
         return self._quant_fn(tensor, config)
 
+    # -- QuantizeFusionPass + QuantizeSimplifyPass on the traced topology ---------------------------------------------------------
+    def _upstream(self, op: QuantableOperation):
+        return [s for s in op.sources if s is not None]
+
+    def _fuse_into_activation(self, producer: QuantableOperation, act: QuantableOperation):
+        if len(producer.consumers) == 1 and len(self._upstream(act)) == 1:                     # refine.py:203-208, 301-306
+            producer.output_cfg.dominated_by = act.output_cfg
+            act.input_cfgs[0].dominated_by = act.output_cfg
+
+    def _fusion_pass(self):
+        ops = [self.operations[n] for n in self._order]
+        for op in ops:                                                  # computing op -> activation (refine.py:186-208)
+            if op.kind in COMPUTING_OP:
+                for act, idx in op.consumers:
+                    if act.kind in ACTIVATION_FUSION_TYPES and idx == 0: self._fuse_into_activation(op, act)
+        for op in ops:                                                  # passive operations share their first input's config (:278-291)
+            if op.kind in PASSIVE_OPERATIONS and op.input_cfgs and op.sources[0] is not None:
+                op.output_cfg.dominated_by = op.input_cfgs[0]
+        for op in ops:                                                  # anything -> Relu / Clip (:293-306)
+            for act, idx in op.consumers:
+                if act.kind in ('Relu', 'Clip') and idx == 0: self._fuse_into_activation(op, act)
+        for op in ops:                                                  # Relu / Clip fed by an invisible (functional / in-place) operation
+            if op.kind in ('Relu', 'Clip') and op.input_cfgs and op.sources[0] is None and op.invisible_source[0]:
+                op.input_cfgs[0].dominated_by = op.output_cfg
+
+    def _simplify_pass(self):
+        for n in self._order:                                           # refine.py:64-88
+            src = self.operations[n]
+            if src.output_cfg.state == QuantizationStates.FP32: continue
+            for dst, idx in src.consumers:
+                cfg = dst.input_cfgs[idx]
+                if cfg.state == QuantizationStates.INITIAL and cfg.is_same_scheme(src.output_cfg):
+                    cfg.dominated_by = src.output_cfg
+
+    # -- forward -----------------------------------------------------------------------------------------------------------------
     def _begin(self):
         self._calls.clear()
         self._collected = []
+        self._restore_weights()
         self._wq = self._quantize_all_weights() if not self._tracing else {}
+
+    def _restore_weights(self):
+        """An operation that raised between its pre- and post-hook leaves the fake-quantised buffer in module.weight: put the fp32 data back."""
+        for module, fp32 in list(self._swapped.items()): module.weight.data = fp32
+        self._swapped.clear()
 
     def _quantize_all_weights(self):
         """All activated per-channel linear weight configs that share (axis, range, rounding) are fake-quantised by ONE multi-tensor launch
@@ -127,48 +217,60 @@ class TorchExecutor:
         outs = self._mw()
         return dict(zip(self._mw_ids, outs))
 
-    def _op_of(self, module) -> QuantableOperation:
+    def _op_of(self, module, num_inputs: int = 1) -> QuantableOperation:
         idx = self._calls.get(id(module), 0)
         name = f'{self._names[id(module)]}#{idx}'
         if self._tracing and name not in self.operations:
-            self.operations[name] = QuantableOperation(name, module, _KINDS[type(module)], is_graph_input=(len(self._order) == 0))
+            self.operations[name] = QuantableOperation(name, module, _KINDS[type(module)], num_inputs)
             self._order.append(name)
         return self.operations[name]
 
+    def _trace_inputs(self, op: QuantableOperation, tensors: List[torch.Tensor]):
+        for i, x in enumerate(tensors):
+            hit, holder = self._produced.get(id(x)), x
+            if hit is None and x._base is not None:                     # a view: passive, shares the producer (and its version counter)
+                hit, holder = self._produced.get(id(x._base)), x._base
+            if hit is None: continue
+            src, _, version = hit
+            if holder._version != version:
+                op.invisible_source[i] = True                          # overwritten in place since (torchvision: `out += identity`)
+                continue
+            op.sources[i] = src
+            src.consumers.append((op, i))
+
     def _pre(self, module, args):
-        op = self._op_of(module)
-        x = args[0]
+        tensors = [a for a in args if isinstance(a, torch.Tensor)]
+        op = self._op_of(module, len(tensors))
         if self._tracing:
-            # conv -> relu fusion: the activation takes over the producer's output config (QuantizeFusionPass)
-            if (op.kind in ('Relu', 'Clip') and self._last_out is not None and self._last_out[1] is x and x._version == self._last_out[2]
-                    and self._last_out[0].kind in ('Conv', 'Gemm')):      # same tensor object AND not modified in place since (residual +=)
-                self._last_out[0].output_cfg.state = QuantizationStates.OVERLAPPED
+            self._trace_inputs(op, tensors)
             return None
         hook = self._hooks.get(op.name) if self._hooks else None
         inputs, qinputs, cfgs = [], [], []
-        if op.input_cfg is not None:
-            inputs.append(x); qinputs.append(self.quantize_function(x, op.input_cfg)); cfgs.append(op.input_cfg)
-            if self._collect and op.input_cfg.state == QuantizationStates.INITIAL: self._emit(x)
+        for x, cfg in zip(tensors, op.input_cfgs):
+            inputs.append(x); qinputs.append(self.quantize_function(x, cfg)); cfgs.append(cfg)
+            if self._collect and cfg.state == QuantizationStates.INITIAL: self._emit(x)
+        changed = any(q is not x for q, x in zip(qinputs, tensors))
         if op.weight_cfg is not None:
             w = module.weight
             wq = self._wq.get(id(module))                                # re-quantised every forward (torch.py:516-518): multi-tensor launch
             if wq is None: wq = self.quantize_function(w.data, op.weight_cfg)
             inputs.append(w.data); qinputs.append(wq); cfgs.append(op.weight_cfg)
             if wq is not w.data:
-                module.__dict__['_ppq_fp32_weight'] = w.data
+                self._swapped[module] = w.data
                 w.data = wq
         if hook is not None: hook.pre_forward_hook(inputs=inputs, quant_inputs=qinputs, quant_configs=cfgs)
-        if op.input_cfg is not None and qinputs[0] is not x:
-            return (qinputs[0],) + tuple(args[1:])
+        if changed:
+            it = iter(qinputs)
+            return tuple(next(it) if isinstance(a, torch.Tensor) else a for a in args)
         return None
 
     def _post(self, module, args, output):
         op = self._op_of(module)
         self._calls[id(module)] = self._calls.get(id(module), 0) + 1
         if self._tracing:
-            self._last_out = (op, output, output._version)
+            self._produced[id(output)] = (op, output, output._version)
             return None
-        fp32 = module.__dict__.pop('_ppq_fp32_weight', None)
+        fp32 = self._swapped.pop(module, None)
         if fp32 is not None: module.weight.data = fp32
         qout = self.quantize_function(output, op.output_cfg)
         hook = self._hooks.get(op.name) if self._hooks else None
@@ -188,7 +290,10 @@ class TorchExecutor:
         returns False leaves the tensor in the collected list instead)."""
         self._hooks, self._collect, self._sink = hooks, collect or sink is not None, sink
         self._begin()
-        out = self.model(inputs)
+        try:
+            out = self.model(inputs)
+        finally:
+            self._restore_weights()                                       # an op that raised must not leave a fake-quantised weight behind
         collected, self._collected, self._sink = self._collected, None, None
         return (out, collected) if collect else out
 
@@ -197,7 +302,7 @@ class TorchExecutor:
         cfgs = []
         for n in self._order:
             op = self.operations[n]
-            if op.input_cfg is not None and op.input_cfg.state == QuantizationStates.INITIAL: cfgs.append(op.input_cfg)
+            cfgs += [c for c in op.input_cfgs if c.state == QuantizationStates.INITIAL]
             if op.output_cfg.state == QuantizationStates.INITIAL: cfgs.append(op.output_cfg)
         return cfgs
 
@@ -206,7 +311,7 @@ class TorchExecutor:
         cfgs = []
         for n in self._order:
             op = self.operations[n]
-            if op.input_cfg is not None: cfgs.append(op.input_cfg)
+            cfgs += [c for c in op.input_cfgs if c.state != QuantizationStates.OVERLAPPED]
             if op.output_cfg.state != QuantizationStates.OVERLAPPED: cfgs.append(op.output_cfg)
         return cfgs
 
@@ -223,13 +328,57 @@ class TorchExecutor:
                 ob.render_quantization_config()
 
     @torch.no_grad()
-    def bake_parameters(self):
-        """ParameterBakingPass (optim/baking.py:34-47, IR/quantize.py:98-111): quantise each weight once and freeze it."""
+    def align_quantization(self, force_overlap: bool = True):
+        """QuantAlignmentPass for element-wise operations, 'Align to Large' (optim/refine.py:443-482, 498-546; the default setting
+        api/setting.py:251-256 has force_alignment_overlap = True): the first input config becomes the PASSIVE master of the op's
+        inputs with the scale of the widest input range; with force_overlap (or a single consumer) the producers' output configs are
+        slaved to it as well, so the tensors are quantised once, with the shared scale, where they are produced."""
+        from .core import QuantizationProperty as P
+        ext = self._ext()
         for n in self._order:
             op = self.operations[n]
-            if op.weight_cfg is not None and op.weight_cfg.state == QuantizationStates.ACTIVATED:
-                op.module.weight.data = self._quant_fn(op.module.weight.data, op.weight_cfg)
-                op.weight_cfg.state = QuantizationStates.BAKED
+            if op.kind not in ELEMENTWISE_ALIGNMENT_TYPES or not op.input_cfgs: continue
+            master = op.input_cfgs[0]
+            los, his = [], []
+            for cfg in op.input_cfgs:
+                if cfg.state == QuantizationStates.FP32 or cfg.policy.has_property(P.FLOATING): continue
+                assert cfg.policy.has_property(P.PER_TENSOR), 'Quant Alignment can only happen with per tensor quantization.'
+                s, o = cfg.scale.float().reshape(()), cfg.offset.float().reshape(())
+                los.append(s * (cfg.quant_min - o)); his.append(s * (cfg.quant_max - o))     # fp32 products, as upstream's tensors
+            zero = torch.zeros((), dtype=torch.float32, device=master.scale.device)
+            lo = torch.minimum(torch.stack(los).min(), zero).reshape(1)                     # global_min / global_max start from 0
+            hi = torch.maximum(torch.stack(his).max(), zero).reshape(1)
+            scale, offset = ext.MinMax_To_Scale_Offset(lo, hi, 1, master.quant_min, master.quant_max, master.policy.has_property(P.SYMMETRICAL),
+                                                       master.policy.has_property(P.POWER_OF_2), _min_scale_of(master))
+            master._dominator = master
+            master.state = QuantizationStates.PASSIVE
+            master.scale, master.offset = scale.squeeze(0), offset.squeeze(0)
+            for slave in op.input_cfgs[1:]:
+                slave.master_by = master
+            for src in self._upstream(op):
+                if len(src.consumers) != 1 and not force_overlap: continue
+                if any(dst is op for dst, _ in src.consumers): src.output_cfg.master_by = master
+
+    @staticmethod
+    def _ext():
+        from .ffi import CUDA_COMPLIER
+        return CUDA_COMPLIER.CUDA_EXTENSION
+
+    @torch.no_grad()
+    def bake_parameters(self):
+        """ParameterBakingPass (optim/baking.py:34-47, IR/quantize.py:98-111): every ACTIVATED / PASSIVE parameter is replaced IN PLACE by its
+        fake-quantised value and its config becomes BAKED / PASSIVE_BAKED, so that later forwards use the value as is."""
+        for n in self._order:
+            op = self.operations[n]
+            cfg = op.weight_cfg
+            if cfg is None or cfg.state not in (QuantizationStates.ACTIVATED, QuantizationStates.PASSIVE): continue
+            op.module.weight.data = self._quant_fn(op.module.weight.data, cfg)
+            cfg.state = QuantizationStates.BAKED if cfg.state == QuantizationStates.ACTIVATED else QuantizationStates.PASSIVE_BAKED
+
+
+def _min_scale_of(cfg) -> float:
+    from .core import OBSERVER_MIN_SCALE, OBSERVER_MIN_SCALE_MANUL_OVERRIDE
+    return cfg.detail.get(OBSERVER_MIN_SCALE_MANUL_OVERRIDE, OBSERVER_MIN_SCALE)
 
 
 # ------------------------------------------------------------------------------------------------------------------ calibration drivers
