@@ -121,7 +121,9 @@ PPQ_B200_API int ppq_b200_histogram_t_dscale(const float *x, int64_t n, const fl
                                              int32_t *hist, int64_t bins, void *stream);
 
 /* replaces Quantile_T, sort.cu:6-20, 42-59 (ffi.py:171-176): out[0] = sorted[clip(rn(n*q))], out[1] = sorted[clip(rn(n*(1-q)))],
- * found by an exact 3-pass radix select on the order-preserving key (no clone, no full sort; same element bit for bit).
+ * found by an exact radix select on the order-preserving key (no clone, no full sort; same element bit for bit): two streaming passes
+ * over the tensor (top-digit histogram, then compaction of the two selected buckets) and a finish over the compacted keys; a third
+ * pass only when a selected bucket does not fit the workspace and holds more than one distinct value.
  * `workspace` is DEVICE scratch of ppq_b200_quantile_workspace_bytes() bytes. */
 PPQ_B200_API int64_t ppq_b200_quantile_workspace_bytes(void);
 PPQ_B200_API int ppq_b200_quantile_t(const float *x, int64_t n, float q, float *out2, void *workspace, void *stream);
@@ -144,6 +146,14 @@ PPQ_B200_API int ppq_b200_multi_minmax_t(const ppq_b200_tensor_desc *descs, int 
 PPQ_B200_API int ppq_b200_multi_histogram_t(const ppq_b200_tensor_desc *descs, int count, int64_t max_n,
                                             const float *hist_scale_arena, int clip_outliers,
                                             int32_t *hist_arena, int64_t bins, void *stream);
+/* Quantile_T (sort.cu:6-20, 42-59) for a table of tensors, one launch per pass: what TorchPercentileObserver.observe
+ * (ppq/quantization/observer/range.py:338-349) asks for once per observed tensor and batch.  Tensor i writes
+ * out[slot_i * out_stride + {0, 1}] = {sorted[clip(rn(n q))], sorted[clip(rn(n (1 - q)))]}.  `cap` = keys of a selected bucket the
+ * workspace can hold per rank (bigger buckets are refined by a further streaming pass instead);
+ * `workspace` is DEVICE scratch of ppq_b200_multi_quantile_workspace_bytes(count, cap) bytes. */
+PPQ_B200_API int64_t ppq_b200_multi_quantile_workspace_bytes(int count, int64_t cap);
+PPQ_B200_API int ppq_b200_multi_quantile_t(const ppq_b200_tensor_desc *descs, int count, int64_t max_n, float q,
+                                           float *out, int64_t out_stride, void *workspace, int64_t cap, void *stream);
 
 /* ---- scale / offset search on the device ---------------------------------------------------------------------- */
 /* replaces minmax_to_scale_offset, ppq/quantization/observer/range.py:22-75, vectorised over `count` ranges

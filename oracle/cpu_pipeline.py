@@ -34,9 +34,10 @@ ELEMENTWISE = {'Add', 'Sub', 'Sum'}
 def _kind(m):
     table = {torch.nn.Conv2d: 'Conv', torch.nn.Linear: 'Gemm', torch.nn.ReLU: 'Relu', torch.nn.ReLU6: 'Clip', torch.nn.MaxPool2d: 'MaxPool',
              torch.nn.AdaptiveAvgPool2d: 'GlobalAveragePool', torch.nn.AvgPool2d: 'AveragePool', torch.nn.Flatten: 'Flatten'}
-    k = table.get(type(m))
-    if k is None and type(m).__name__ in ('Add', 'Concat'): k = type(m).__name__       # element-wise ops written as modules
-    return k
+    for t in type(m).__mro__:
+        if t in table: return table[t]
+        if t.__name__ in ('Add', 'Concat') and t.__module__ != 'torch.nn.modules.module': return t.__name__      # element-wise ops written as modules
+    return None
 
 
 def _fuse_bn(model):

@@ -19,7 +19,8 @@ from typing import Callable, Dict, Iterable, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-from .core import OBSERVER_KL_HIST_BINS, OBSERVER_MIN_SCALE, QuantizationProperty, QuantizationStates
+from .core import (OBSERVER_KL_HIST_BINS, OBSERVER_MIN_SCALE, OBSERVER_MSE_COMPUTE_INTERVAL, OBSERVER_MSE_HIST_BINS, OBSERVER_PERCENTILE,
+                   QuantizationProperty, QuantizationStates)
 
 
 # ---- the two exchange steps (pure torch.distributed; CPU/gloo-testable) --------------------------------------------------------
@@ -76,49 +77,113 @@ def shard_indices(num_samples: int, rank: int, world_size: int) -> range:
 
 
 # ---- arena calibrator -------------------------------------------------------------------------------------------------------------
+class DescriptorStager:
+    """Host -> device upload of small descriptor tables without cudaHostAlloc on the hot path: a ring of persistent pinned staging
+    buffers (an event per slot guards reuse), cudaMemcpyAsync on the current stream.  Tables are cached by content (LRU)."""
+
+    def __init__(self, device, columns: int, rows: int = 256, ring: int = 8, cache: int = 128):
+        self.device, self.columns, self.ring, self.cache_size = torch.device(device), columns, ring, cache
+        self._rows = rows
+        self._host = [self._alloc(rows) for _ in range(ring)] if self.device.type == 'cuda' else None
+        self._events, self._k, self._cache = [None] * ring, 0, {}
+
+    def _alloc(self, rows):
+        return torch.empty(rows, self.columns, dtype=torch.int64).pin_memory()
+
+    def get(self, key: tuple) -> torch.Tensor:
+        """key: tuple of row tuples (ints).  Returns the [len(key), columns] int64 device tensor holding it."""
+        hit = self._cache.pop(key, None)
+        if hit is None:
+            table = torch.tensor(key, dtype=torch.int64).reshape(len(key), self.columns)
+            if self._host is None:
+                hit = table.to(self.device)
+            else:
+                if len(key) > self._rows:                                # grow every slot once (rare: a bigger network than sized for)
+                    torch.cuda.synchronize(self.device)
+                    self._rows = max(len(key), 2 * self._rows)
+                    self._host = [self._alloc(self._rows) for _ in range(self.ring)]
+                    self._events = [None] * self.ring
+                i = self._k % self.ring; self._k += 1
+                if self._events[i] is not None: self._events[i].synchronize()
+                stage = self._host[i][:len(key)]
+                stage.copy_(table)
+                hit = torch.empty(len(key), self.columns, dtype=torch.int64, device=self.device)
+                hit.copy_(stage, non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(self.device)); self._events[i] = ev
+            while len(self._cache) >= self.cache_size: self._cache.pop(next(iter(self._cache)))      # evict the least recently used
+        self._cache[key] = hit                                            # (re-)insert as most recent
+        return hit
+
+
 class ArenaCalibrator:
-    def __init__(self, num_tensors: int, device, bins: int = OBSERVER_KL_HIST_BINS, num_of_bits: int = 8,
+    """method:  'minmax'      one phase: fused min/max                       -> MinMax_To_Scale_Offset
+                'kl'          + phase 2: 4096-bin histogram                  -> KL_Search
+                'mse'         + phase 2: 2048-bin histogram                  -> MSE_Search (symmetric configs; range.py:406-520)
+                'percentile'  one phase: Quantile_T of every tensor and batch (ONE multi-tensor select per forward), fp32 mean over the
+                              batches in sample order                        -> MinMax_To_Scale_Offset   (range.py:312-403)"""
+
+    def __init__(self, num_tensors: int, device, bins: int = None, num_of_bits: int = 8,
                  quant_min: int = -128, quant_max: int = 127, power_of_2: bool = False, min_scale: float = OBSERVER_MIN_SCALE,
-                 method: str = 'kl', group=None):
+                 method: str = 'kl', group=None, percentile: float = OBSERVER_PERCENTILE, select_cap: int = 1 << 16):
         from .ffi import extension
-        assert method in ('kl', 'minmax')
+        if method not in ('kl', 'minmax', 'mse', 'percentile'):
+            raise ValueError(f"ArenaCalibrator: unknown observer algorithm {method!r} (expected 'kl', 'minmax', 'mse' or 'percentile')")
+        if bins is None: bins = OBSERVER_MSE_HIST_BINS if method == 'mse' else OBSERVER_KL_HIST_BINS
         self.ext = extension()
         self.T, self.bins, self.device, self.group = num_tensors, bins, torch.device(device), group
         self.num_of_bits, self.quant_min, self.quant_max = num_of_bits, quant_min, quant_max
         self.power_of_2, self.min_scale, self.method = power_of_2, min_scale, method
+        self.percentile, self.select_cap = percentile, select_cap
         self.minmax = torch.empty(num_tensors, 2, dtype=torch.float32, device=self.device)
-        self.hist = torch.zeros(num_tensors, bins, dtype=torch.int32, device=self.device)
+        two_phase = method in ('kl', 'mse')
+        self.hist = torch.zeros(num_tensors, bins if two_phase else 1, dtype=torch.int32, device=self.device)
         self.hist_scale = torch.zeros(num_tensors, dtype=torch.float32, device=self.device)
         self.scale = self.offset = self.best_bin_range = None
-        self._desc_cache: Dict[tuple, tuple] = {}
+        self._stager = DescriptorStager(self.device, 3, rows=max(num_tensors, 16))
+        self._pct: List[torch.Tensor] = []                               # per batch: [T, 2] {upper, lower} quantiles
+        self._select_ws = None
+        self.exchange_events = None                                      # set to a dict to time the exchange steps with CUDA events
         self.launches = 0
         self.reset()
 
     def reset(self):
         self.minmax[:, 0] = float('inf'); self.minmax[:, 1] = float('-inf')
         self.hist.zero_()
+        self._pct = []
         self.phase = 1
 
     def _descs(self, tensors: Sequence[torch.Tensor], slots: Optional[Sequence[int]] = None):
         if slots is None:
             assert len(tensors) == self.T, f'expected {self.T} tensors per forward, got {len(tensors)}'
             slots = range(self.T)
+        for t in tensors:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise RuntimeError('ArenaCalibrator needs contiguous fp32 CUDA tensors')
         key = tuple((t.data_ptr(), t.numel(), i) for t, i in zip(tensors, slots))
-        hit = self._desc_cache.get(key)
-        if hit is None:
-            for t in tensors:
-                if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
-                    raise RuntimeError('ArenaCalibrator needs contiguous fp32 CUDA tensors')
-            host = torch.tensor([[p, n, i] for (p, n, i) in key], dtype=torch.int64).pin_memory()
-            hit = (host.to(self.device, non_blocking=True), max(n for _, n, _ in key))
-            if len(self._desc_cache) < 64: self._desc_cache[key] = hit
-        return hit
+        return self._stager.get(key), max(k[1] for k in key)
+
+    def begin_batch(self):
+        """Call before every forward: the percentile observer keeps one {upper, lower} row per batch (range.py:349), whatever number of
+        launches the forward's tensors are observed with."""
+        if self.method == 'percentile':
+            self._pct.append(torch.zeros(self.T, 2, dtype=torch.float32, device=self.device))
+
+    def _batch_quantiles(self) -> torch.Tensor:
+        if not self._pct: self.begin_batch()
+        return self._pct[-1]
 
     @torch.no_grad()
     def observe(self, tensors: Sequence[torch.Tensor], slots: Optional[Sequence[int]] = None):
         """One multi-tensor launch over `tensors`; tensor j accumulates into arena slot slots[j] (default: j)."""
         if len(tensors) == 0: return
         descs, max_n = self._descs(tensors, slots)
+        if self.method == 'percentile':
+            need = self.ext.Multi_Quantile_Workspace_Bytes(len(tensors), self.select_cap)
+            if self._select_ws is None or self._select_ws.numel() < need:
+                self._select_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self.ext.Multi_Quantile_T(descs, max_n, self.percentile, self._batch_quantiles(), 2, self._select_ws, self.select_cap)
+            self.launches += 8
+            return
         if self.phase == 1:
             self.ext.Multi_MinMax_T(descs, max_n, self.minmax)
         else:
@@ -129,6 +194,10 @@ class ArenaCalibrator:
     def observe_one(self, index: int, tensor: torch.Tensor):
         """Immediate single-tensor collection into slot `index` (used while a forward is running: later in-place ops of the
         network may overwrite the tensor, so it cannot wait for the end-of-forward multi-tensor launch)."""
+        if self.method == 'percentile':
+            self._batch_quantiles()[index].copy_(self.ext.Quantile_T(tensor, self.percentile))
+            self.launches += 5
+            return
         if self.phase == 1:
             self.ext.MinMax_T(tensor, self.minmax[index])
         else:
@@ -138,7 +207,7 @@ class ArenaCalibrator:
     def _timed_exchange(self, name: str):
         """CUDA events around one exchange step when `self.exchange_events` is a dict (bench.py's scaling report), else a no-op."""
         import contextlib
-        ev = getattr(self, 'exchange_events', None)
+        ev = self.exchange_events
         if ev is None or not self.minmax.is_cuda: return contextlib.nullcontext()
 
         @contextlib.contextmanager
@@ -150,26 +219,47 @@ class ArenaCalibrator:
             ev.setdefault(name, []).append((a, b))
         return ctx()
 
+    def _distributed(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
     @torch.no_grad()
     def end_phase(self):
         """Exchange + render of the finished phase.  Returns True when calibration is complete."""
+        sym = True                                                       # the arena serves per-tensor symmetric activation configs
+        if self.method == 'percentile':
+            if not self._pct: raise ValueError('Can not render quantization config yet, Observer data collator is empty.')
+            rows = torch.stack(self._pct, dim=1)                         # [T, batches, 2]
+            if self._distributed():
+                with self._timed_exchange('percentile'):
+                    rows = gather_in_sample_order(rows, self.group)
+            # fp32 mean over the batches, per tensor on a contiguous [batches, 2] block: the reduction the reference runs
+            # (torch.cat(collector, dim=0).float().mean(dim=0), range.py:369), so the summation order is torch's for that shape
+            mean = torch.stack([rows[t].mean(dim=0) for t in range(rows.shape[0])])
+            self.scale, self.offset = self.ext.MinMax_To_Scale_Offset(mean[:, 1].contiguous(), mean[:, 0].contiguous(), 1, self.quant_min,
+                                                                      self.quant_max, sym, self.power_of_2, self.min_scale)
+            self.launches += 1
+            return True
         if self.phase == 1:
             with self._timed_exchange('minmax'):
                 allreduce_minmax(self.minmax, self.group)
             if self.method == 'minmax':
                 self.scale, self.offset = self.ext.MinMax_To_Scale_Offset(self.minmax.view(-1), self.minmax.view(-1)[1:], 2, self.quant_min,
-                                                                          self.quant_max, True, self.power_of_2, self.min_scale)
+                                                                          self.quant_max, sym, self.power_of_2, self.min_scale)
                 self.launches += 1
                 return True
-            self.hist_scale = self.ext.Hist_Scale_From_MinMax(self.minmax, True, self.bins)
+            self.hist_scale = self.ext.Hist_Scale_From_MinMax(self.minmax, sym, self.bins)
             self.launches += 1
             self.phase = 2
             return False
         with self._timed_exchange('hist'):
             allreduce_hist(self.hist, self.group)
-        self.scale, self.best_bin_range = self.ext.KL_Search(self.hist, self.bins, self.hist_scale, self.minmax, self.num_of_bits,
-                                                             self.power_of_2, self.min_scale)
-        self.offset = torch.zeros_like(self.scale)
+        if self.method == 'kl':
+            self.scale, self.best_bin_range = self.ext.KL_Search(self.hist, self.bins, self.hist_scale, self.minmax, self.num_of_bits,
+                                                                 self.power_of_2, self.min_scale)
+            self.offset = torch.zeros_like(self.scale)
+        else:
+            self.scale, self.offset = self.ext.MSE_Search(self.hist, self.bins, self.minmax, self.quant_min, self.quant_max, sym,
+                                                          self.power_of_2, self.min_scale, OBSERVER_MSE_COMPUTE_INTERVAL)
         self.launches += 1
         return True
 
@@ -247,21 +337,44 @@ class RuntimeCalibrationPass:
             if calib_step >= self._calib_steps: break
 
     def _reduce(self, phase: int):
+        """The exchange step of a phase: every statistic of every observer is made global before render (SURVEY 8e).  Per-tensor {min, max}
+        and per-channel min / max vectors travel in ONE packed MAX all-reduce ({-min, max}: exact), histograms in ONE SUM all-reduce,
+        per-batch percentile pairs in an all-gather re-ordered by sample."""
         from .observer import TorchHistObserver, TorchMinMaxObserver, TorchPercentileObserver
-        obs = [ob for o in self._observers.values() for ob in o.hook._observer_table.values()]
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(self._group) > 1): return
+        obs = [ob for o in self._observers.values() for ob in o.hook._observer_table.values()]
         if phase == 1:
-            pct = [ob for ob in obs if isinstance(ob, TorchPercentileObserver) and ob._percentile_collector]
+            pct = [ob for ob in obs if isinstance(ob, TorchPercentileObserver)]
+            mm = [ob for ob in obs if isinstance(ob, TorchMinMaxObserver)]
+            # a rank whose shard was empty has no statistics (and no slots): the collectives below would mismatch or hang, so agree on it first
+            fed = all(ob._observed > 0 for ob in mm) and all(len(ob._percentile_collector) > 0 for ob in pct)
+            dev = next((ob._slot.minmax.device for ob in mm if ob._slot is not None), None)
+            if dev is None: dev = next((ob._percentile_collector[0].device for ob in pct if ob._percentile_collector), torch.device('cpu'))
+            if dist.get_backend(self._group) == 'nccl' and dev.type != 'cuda': dev = torch.device('cuda', torch.cuda.current_device())
+            flag = torch.tensor([1 if fed else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._group)
+            if int(flag.item()) == 0:
+                raise RuntimeError('RuntimeCalibrationPass: at least one rank observed no calibration batch (fewer batches than ranks?); '
+                                   'every rank needs >= 1 batch of its shard before the statistics can be reduced.')
             if pct:
                 # the percentile observer averages per-batch quantile pairs in fp32 (range.py:369): gather every rank's pairs and put
                 # them back in global sample order, so the mean is the same sum, in the same order, as the single-process run
                 merged = gather_in_sample_order(torch.stack([torch.cat(ob._percentile_collector, dim=0) for ob in pct]), self._group)
                 for ob, rows in zip(pct, merged): ob._percentile_collector = [rows]
-            mm = [ob for ob in obs if isinstance(ob, TorchMinMaxObserver) and ob._slot is not None and ob._slot.cmins is None]
             if mm:
-                buf = torch.stack([ob._slot.minmax for ob in mm])
-                allreduce_minmax(buf, self._group)
-                for ob, row in zip(mm, buf): ob._slot.minmax.copy_(row)
+                parts = []
+                for ob in mm:
+                    if ob._slot.cmins is None: parts += [-ob._slot.minmax[0:1], ob._slot.minmax[1:2]]
+                    else: parts += [-ob._slot.cmins, ob._slot.cmaxs]
+                buf = torch.cat(parts)
+                dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=self._group)
+                at = 0
+                for ob in mm:
+                    if ob._slot.cmins is None:
+                        ob._slot.minmax[0:1].copy_(-buf[at:at + 1]); ob._slot.minmax[1:2].copy_(buf[at + 1:at + 2]); at += 2
+                    else:
+                        C = ob._slot.cmins.numel()
+                        ob._slot.cmins.copy_(-buf[at:at + C]); ob._slot.cmaxs.copy_(buf[at + C:at + 2 * C]); at += 2 * C
         else:
             hs = [ob for ob in obs if isinstance(ob, TorchHistObserver) and ob._slot is not None]
             if hs:

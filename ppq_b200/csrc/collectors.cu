@@ -353,7 +353,7 @@ constexpr int kMaxSmemBins = 12287;            // (bins + 1) int32 slots within 
 static inline int hist_grid(int64_t n, int bins) {
     const int64_t per_cta = (int64_t)bins * 16 > 65536 ? (int64_t)bins * 16 : 65536;
     int64_t g = (n + per_cta - 1) / per_cta;
-    const int64_t cap = (int64_t)kSMs;
+    const int64_t cap = (int64_t)sm_count();
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
@@ -369,10 +369,10 @@ static int launch_hist(const float *x, int64_t n, const BinParams &bin, int64_t 
     case 1:  histogram_kernel<1, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     case 2:  histogram_kernel<2, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     case 3:  histogram_kernel<3, Bin, kUnroll, kThreads><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
-    case 4:  histogram_kernel<0, Bin, 8, kThreads><<<grid * 8 > kSMs * 8 ? kSMs * 8 : grid * 8, kThreads, smem, st>>>(x, n, bin, hist); break;   // the round-1 small-CTA layout
+    case 4:  histogram_kernel<0, Bin, 8, kThreads><<<grid * 8 > sm_count() * 8 ? sm_count() * 8 : grid * 8, kThreads, smem, st>>>(x, n, bin, hist); break;   // the round-1 small-CTA layout
     // 5 / 6: two 1024-thread CTAs per SM (32 registers per thread), 2 / 4 loads in flight per thread
-    case 5:  histogram_kernel<0, Bin, 2, kHistThreads, 2><<<grid * 2 > kSMs * 2 ? kSMs * 2 : grid * 2, kHistThreads, smem, st>>>(x, n, bin, hist); break;
-    case 6:  histogram_kernel<0, Bin, 4, kHistThreads, 2><<<grid * 2 > kSMs * 2 ? kSMs * 2 : grid * 2, kHistThreads, smem, st>>>(x, n, bin, hist); break;
+    case 5:  histogram_kernel<0, Bin, 2, kHistThreads, 2><<<grid * 2 > sm_count() * 2 ? sm_count() * 2 : grid * 2, kHistThreads, smem, st>>>(x, n, bin, hist); break;
+    case 6:  histogram_kernel<0, Bin, 4, kHistThreads, 2><<<grid * 2 > sm_count() * 2 ? sm_count() * 2 : grid * 2, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     default: histogram_kernel<0, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     }
     return (int)cudaGetLastError();
@@ -404,7 +404,7 @@ int ppq_b200_minmax_c(const float *x, int64_t n, int64_t epc, int C, float *mins
     if (chunks > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
     const int64_t items = rows * chunks;
     int64_t grid = (items + (kThreads / 32) - 1) / (kThreads / 32);
-    if (grid > (int64_t)kSMs * 8) grid = (int64_t)kSMs * 8;
+    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
     minmax_c_kernel<<<(int)grid, kThreads, 0, (cudaStream_t)stream>>>(x, rows, epc, C, chunks, FastDiv((uint32_t)chunks),
                                                                           FastDiv((uint32_t)C), mins, maxs);
     return (int)cudaGetLastError();
@@ -438,7 +438,7 @@ int ppq_b200_histogram_c(const float *x, int64_t n, int64_t epc, int C, float hi
     const int64_t chunk = (int64_t)bins * 8 > 32768 ? (int64_t)bins * 8 : 32768;
     const int64_t chunks = (epc + chunk - 1) / chunk;
     const int64_t items = rows * chunks;
-    const int grid = (int)(items < (int64_t)kSMs * 8 ? items : (int64_t)kSMs * 8);
+    const int grid = (int)(items < (int64_t)sm_count() * 8 ? items : (int64_t)sm_count() * 8);
     histogram_c_kernel<0><<<grid, kThreads, (size_t)(bins + 1) * sizeof(int), (cudaStream_t)stream>>>(
         x, rows, epc, C, chunk, chunks, hist_scale, clip_outliers, (int)bins, hist);
     return (int)cudaGetLastError();
@@ -450,7 +450,7 @@ int ppq_b200_multi_minmax_t(const ppq_b200_tensor_desc *descs, int count, int64_
     const int64_t cpt = (max_n + chunk - 1) / chunk;
     if (cpt > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
     const int64_t items = (int64_t)count * cpt;
-    const int grid = (int)(items < (int64_t)kSMs * 8 ? items : (int64_t)kSMs * 8);
+    const int grid = (int)(items < (int64_t)sm_count() * 8 ? items : (int64_t)sm_count() * 8);
     multi_minmax_t_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(descs, count, chunk, (int)cpt, minmax_arena);
     return (int)cudaGetLastError();
 }
@@ -462,7 +462,7 @@ int ppq_b200_multi_histogram_t(const ppq_b200_tensor_desc *descs, int count, int
     if (smem > 48 * 1024) return (int)cudaErrorInvalidValue;
     // grid: one CTA per SM, fewer when the whole job is small (each CTA should own >= 64 Ki elements before paying for a flush)
     int64_t g = ((int64_t)count * max_n + 65535) / 65536;
-    if (g > kSMs) g = kSMs;
+    if (g > sm_count()) g = sm_count();
     if (g < 1) g = 1;
     multi_histogram_t_kernel<0><<<(int)g, kHistThreads, smem, (cudaStream_t)stream>>>(descs, count, hist_scale_arena, clip_outliers, (int)bins,
                                                                                       hist_arena);

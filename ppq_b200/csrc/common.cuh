@@ -10,7 +10,18 @@
 
 namespace ppqb {
 
-constexpr int kSMs = 148;                      // B200: 2 dies x 74 SMs
+// SM count of the CURRENT device (B200: 148 = 2 dies x 74), queried once per device ordinal; every persistent grid is sized from it.
+inline int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cached[dev];
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev] = v;
+    }
+    return v;
+}
 constexpr int RND_HALF_EVEN = 0, RND_HALF_UP = 1, RND_HALF_DOWN = 2, RND_HALF_TOWARDS_ZERO = 3,
               RND_HALF_FAR_FROM_ZERO = 4, RND_TO_NEAR_INT = 5, RND_UP = 6, RND_DOWN = 7;
 
@@ -190,7 +201,7 @@ __device__ __forceinline__ void atomic_min_float(float *addr, float v) {
 inline int grid_for(int64_t work_items, int threads, int items_per_thread, int ctas_per_sm) {
     const int64_t per_cta = (int64_t)threads * items_per_thread;
     int64_t g = (work_items + per_cta - 1) / per_cta;
-    const int64_t cap = (int64_t)kSMs * ctas_per_sm;
+    const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;

@@ -503,7 +503,7 @@ int ppq_b200_multi_linear_quant_c(const ppq_b200_lc_desc *descs, int count, int6
     if (count <= 0 || count > kMaxMultiTensors || max_n <= 0 || max_n > 0x7fffffffLL || !descs || qmin > qmax) return (int)cudaErrorInvalidValue;
     // upper bound of the work (the true total is summed on the device): one CTA per 8 segments of 512 elements, at most 8 CTAs per SM
     int64_t g = ((int64_t)count * ((max_n + 4 * kSegVec - 1) / (4 * kSegVec)) + 7) / 8;
-    if (g > (int64_t)kSMs * 8) g = (int64_t)kSMs * 8;
+    if (g > (int64_t)sm_count() * 8) g = (int64_t)sm_count() * 8;
     const size_t smem = (size_t)(count + 1) * sizeof(long long);
     if (rounding == RND_HALF_EVEN) multi_channel_kernel<LinearOp<0>><<<(int)g, kThreads, smem, (cudaStream_t)stream>>>(descs, count, {qmin, qmax, 0});
     else multi_channel_kernel<LinearOp<-1>><<<(int)g, kThreads, smem, (cudaStream_t)stream>>>(descs, count, {qmin, qmax, rounding});

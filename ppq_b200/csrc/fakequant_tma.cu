@@ -135,15 +135,13 @@ using namespace ppqb;
 
 int launch_linear_quant_t_tma(const float *x, float *y, int64_t n, const float *scale, const float *offset,
                               int qmin, int qmax, cudaStream_t st) {
-    static bool configured = false;
     const int smem = kStages * kTileBytes + 2 * kStages * (int)sizeof(uint64_t);
-    if (!configured) {
-        cudaFuncSetAttribute(linear_quant_t_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = true;
-    }
+    // the > 48 KB opt-in is per device, not per process: set it on every launch of this (non-default) variant
+    if (cudaFuncSetAttribute(linear_quant_t_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return (int)cudaGetLastError();
     const int64_t n4 = n >> 2;
     const int64_t tiles = (n4 + kTileVec - 1) / kTileVec;
-    int64_t grid = (int64_t)kSMs * 3;
+    int64_t grid = (int64_t)sm_count() * 3;
     if (grid > tiles) grid = tiles;
     if (grid < 1) grid = 1;
     linear_quant_t_tma_kernel<<<(int)grid, kTmaThreads, smem, st>>>(x, y, n, scale, offset, qmin, qmax);

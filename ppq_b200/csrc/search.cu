@@ -20,21 +20,21 @@ namespace ppqb {
 __device__ __forceinline__ double round_half_even(double v) { return rint(v); }
 
 // ppq_round_to_power_of_2 (utils/round.py:115-135): 2^round(log2(x)); ROUND_UP = ceil, ROUND_HALF_UP on the exponent.
-// ceil(log2 x) is taken from the binary exponent (exact, like Python's math.log2 on powers of two); the result is
-// built with ldexp, so no transcendental rounding can move it.
+// Exact powers of two are recognised from the binary exponent (math.log2 is exact on them); everything else follows the Python formula
+// on the double log2, so a value a few ulps above a power of two rounds the way math.log2 + ceil() does.  The result is built with ldexp.
+// Ties of the HALF_UP policy: Decimal ROUND_HALF_UP for value > 0 (2.5 -> 3) and ROUND_HALF_DOWN for value <= 0 (-9.5 -> -9,
+// utils/round.py:80-82) -- both send an exact .5 to floor + 1.
 __device__ __forceinline__ double pow2_round(double v, bool half_up) {
     if (v == 0.0) return 0.0;
     const double sign = v >= 0.0 ? 1.0 : -1.0;
     int e2;
     const double m = frexp(sign * v, &e2);                             // |v| = m * 2^e2, m in [0.5, 1)
     int e;
-    if (!half_up) e = (m == 0.5) ? e2 - 1 : e2;                        // ceil(log2 |v|)
+    if (m == 0.5) e = e2 - 1;                                           // exact power of two
     else {
-        // Decimal ROUND_HALF_UP for positive exponents, ROUND_HALF_DOWN for negative ones (utils/round.py:80-82)
         const double l = log2(sign * v);
-        const double f = floor(l), frac = l - f;
-        if (m == 0.5) e = e2 - 1;                                       // exact power of two
-        else if (frac > 0.5) e = (int)f + 1; else if (frac < 0.5) e = (int)f; else e = (l > 0.0) ? (int)f + 1 : (int)f;
+        if (!half_up) e = (int)ceil(l);
+        else { const double f = floor(l); e = (l - f >= 0.5) ? (int)f + 1 : (int)f; }
     }
     return sign * ldexp(1.0, e);
 }
@@ -99,13 +99,14 @@ kl_search_kernel(const int32_t *__restrict__ hist_arena, int bins, const float *
                  const float *__restrict__ minmax_arena, int num_of_bits, int pow2, double min_scale, float *__restrict__ scale_out, int32_t *__restrict__ best_out) {
     extern __shared__ unsigned char kl_smem[];
     float *h = reinterpret_cast<float *>(kl_smem);                    // [bins]   the edited histogram as fp32
+    const int pre_len = max(bins + 1, kKlThreads);                    // the prefix array doubles as scratch for the per-thread totals of the scan
     double *pre = reinterpret_cast<double *>(kl_smem + (((size_t)bins * 4 + 7) & ~(size_t)7));   // [bins + 1] exclusive prefix sums
-    float *gval = reinterpret_cast<float *>(pre + bins + 1);          // [quant_bins] per-group spread value, then q of the group
+    float *gval = reinterpret_cast<float *>(pre + pre_len);           // [quant_bins] per-group spread value, then q of the group
     // memo (bins <= kKlMemoBins): log10(p + 1e-30) of every bin is the same for all 32 candidates (only the bin that absorbs the tail
     // differs), and log10(q + 1e-30) is shared by the bins of a group -> 4096 + 32 x 128 fp64 logarithms instead of 2 x 67 584.
     // The doubles that enter the sum are the same ones, in the same order, so the losses are bit-identical to the direct evaluation.
     const bool memo = bins <= kKlMemoBins;
-    double *glogq = reinterpret_cast<double *>(kl_smem + ((((size_t)bins * 4 + 7) & ~(size_t)7) + (size_t)(bins + 1) * 8 +
+    double *glogq = reinterpret_cast<double *>(kl_smem + ((((size_t)bins * 4 + 7) & ~(size_t)7) + (size_t)pre_len * 8 +
                                                           (((size_t)(1 << (num_of_bits - 1)) * 4 + 7) & ~(size_t)7)));   // [quant_bins]
     double *logp = glogq + (1 << (num_of_bits - 1));                                                                    // [bins]
     __shared__ double scratch[kKlThreads / 32];
@@ -306,14 +307,14 @@ int ppq_b200_kl_search(const int32_t *hist_arena, int64_t count, int64_t bins, c
         return (int)cudaErrorInvalidValue;
     if (num_of_bits < 2 || num_of_bits > 16) return (int)cudaErrorInvalidValue;
     const int64_t qb = 1ll << (num_of_bits - 1);
-    if (bins < qb || bins > 16384 || bins < kKlThreads) return (int)cudaErrorInvalidValue;
-    size_t smem = (((size_t)bins * 4 + 7) & ~(size_t)7) + (size_t)(bins + 1) * 8 + (((size_t)qb * 4 + 7) & ~(size_t)7);
+    if (bins < qb || bins > 16384) return (int)cudaErrorInvalidValue;  // OBSERVER_KL_HIST_BINS_MANUL_OVERRIDE: any multiple of the quant bins works
+    const size_t pre_len = (size_t)(bins + 1 > kKlThreads ? bins + 1 : kKlThreads);
+    size_t smem = (((size_t)bins * 4 + 7) & ~(size_t)7) + pre_len * 8 + (((size_t)qb * 4 + 7) & ~(size_t)7);
     if (bins <= kKlMemoBins) smem += (size_t)(qb + bins) * 8;          // memoised logarithms (see the kernel)
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(kl_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        configured = true;
-    }
+    // > 48 KB of dynamic shared memory is an opt-in PER DEVICE: set it on every launch (a process-wide flag would leave the second GPU of a
+    // process without it; the call is a few hundred nanoseconds against a kernel of >= 100 us)
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kl_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+        return (int)cudaGetLastError();
     kl_search_kernel<<<(int)count, kKlThreads, smem, (cudaStream_t)stream>>>(hist_arena, (int)bins, hist_scale_arena, minmax_arena,
                                                                                num_of_bits, power_of_2, min_scale, scale_out, best_bin_range_out);
     return (int)cudaGetLastError();

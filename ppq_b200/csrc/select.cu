@@ -1,31 +1,59 @@
 // select.cu -- exact order statistics without sorting (sm_100a), behind the C ABI of include/ppq_b200.h.
 //
-//   ppq_b200_quantile_t   replaces Quantile_T (/root/reference/ppq/csrc/cuda/sort.cu:6-20, 42-59): the reference clones the
-//                         tensor, thrust::sort's the clone and reads sorted[clip(rn(n*q))] and sorted[clip(rn(n*(1-q)))].
-//   ppq_b200_isotone_t    replaces Isotone_T (sort.cu:23-40, 61-73): sorted[n-1], sorted[n-2], sorted[0], sorted[1].
+//   ppq_b200_quantile_t         replaces Quantile_T (/root/reference/ppq/csrc/cuda/sort.cu:6-20, 42-59): the reference clones the
+//                               tensor, thrust::sort's the clone and reads sorted[clip(rn(n*q))] and sorted[clip(rn(n*(1-q)))].
+//   ppq_b200_multi_quantile_t   the same for a table of tensors in one launch per pass (the percentile observer of the calibration arena:
+//                               TorchPercentileObserver, ppq/quantization/observer/range.py:312-403, is the reference's default observer).
+//   ppq_b200_isotone_t          replaces Isotone_T (sort.cu:23-40, 61-73): sorted[n-1], sorted[n-2], sorted[0], sorted[1].
 //
-// Here: MSD radix *select* on the order-preserving 32-bit key of each float (the same total order thrust's radix sort uses:
-// -NaN < -inf < ... < -0 == +0 < ... < +inf < +NaN; the two zeros share one key, see order_key), 11 + 11 + 10 bits, both requested
-// ranks resolved together.  Three
-// streaming passes over the input (12 B/element, shared-memory privatised digit histograms) instead of a clone plus a full
-// device sort; no allocation -- the caller provides a small workspace.  The result is the identical element, bit for bit, except that a
-// selected zero is always reported as +0.0 (equal as a float to whichever zero the reference's sort left at that index).
+// MSD radix *select* on the order-preserving 32-bit key of each float (the same total order thrust's radix sort uses:
+// -NaN < -inf < ... < -0 == +0 < ... < +inf < +NaN; the two zeros share one key, see order_key), digits of 11 + 11 + 10 bits, both
+// requested ranks resolved together.
+//
+//   pass 0   streams the tensor once (4 B/element): 2048-bin histogram of the top digit, shared-memory privatised.  The scan that ends the
+//            pass knows the population of the bucket each rank fell into.
+//   pass 1   streams the tensor a second time and looks only at elements of the one or two selected buckets (a vector whose four elements
+//            miss both prefixes costs one AND + three compares per element on the raw bits).  The requested ranks sit in the tails
+//            (q = 0.9999), so a bucket normally holds ~1e-4 of the tensor: when it fits the workspace (`cap` keys) its keys are COMPACTED
+//            (staged per CTA in shared memory, one global reservation per CTA) instead of histogrammed, and
+//   finish   one CTA per rank selects among the few thousand compacted keys (L2-resident, KBs) -- no third pass over the tensor.
+//            A bucket too big to compact (post-ReLU tensors: half of the elements are exactly 0) is refined by histogram as before, and
+//            the min / max key of the bucket is tracked on the way: when they coincide the bucket is one repeated value and the rank is
+//            resolved on the spot.  Only a big bucket with several distinct values needs pass 2 (launched always, returns at once when no
+//            rank asks for it).
+// Algorithmic traffic: 4 B/element; this design moves 8 B/element (two streaming passes), the round-1 version 12.
+// No allocation -- the caller provides the workspace.  The result is the identical element, bit for bit, except that a selected zero is
+// always reported as +0.0 (equal as a float to whichever zero the reference's sort left at that index).
 #include "common.cuh"
 #include "../../include/ppq_b200.h"
 
 namespace ppqb {
 
-constexpr int kSelThreads = 1024;
-constexpr int kDigits = 2048;                  // 11-bit digits (the last pass uses 10 bits)
+constexpr int kSelThreads = 1024;              // pass 0: two CTAs per SM
+constexpr int kFilterThreads = 256;            // passes 1-2: six CTAs per SM
+constexpr int kDigits = 2048;                  // 11-bit digits (the last level has 10 bits)
+constexpr int kStage = kDigits;                // keys a CTA stages in shared memory per rank before its global reservation
+constexpr unsigned kModeHist = 0, kModeCompact = 1, kModeDone = 2;
+constexpr int64_t kDefaultCap = 1 << 18;       // single-tensor entry: 256 Ki keys per rank (2 MB of workspace)
 
-struct SelectState {                           // lives in the caller's workspace
+struct SelectState {                           // one per tensor, in the caller's workspace
     unsigned long long hist[2][kDigits];       // per rank: digit histogram of the current pass
-    unsigned int prefix[2];                    // key bits resolved so far (high bits)
-    unsigned int done;                         // CTAs that have flushed their digits in the current pass
-    unsigned int pad_;
-    long long rank[2];                         // remaining rank inside the current prefix bucket
-    long long ranks_in[4];
+    unsigned int prefix[2];                    // key bits resolved so far (high bits); the full key once mode == done
+    unsigned int mode[2];
+    unsigned int shared;                       // both ranks are in the same bucket and mode: rank 1 reads rank 0's histogram / buffer
+    unsigned int done;                         // CTAs that have flushed in the current pass (single-tensor path)
+    unsigned int ccount[2];                    // keys in the compact buffers
+    unsigned int cbuf[2];                      // which buffer holds rank r's candidates
+    unsigned int clevel[2];                    // first unresolved level of the compacted keys
+    unsigned int compacted[2];
+    unsigned int kmin[2], kmax[2];             // min / max key seen in the bucket during a refining pass
+    long long rank[2];                         // remaining rank inside the current bucket
+    long long count[2];                        // population of the current bucket
 };
+
+__host__ __device__ constexpr int level_shift(int level) { return level == 0 ? 21 : (level == 1 ? 10 : 0); }
+__host__ __device__ constexpr uint32_t level_dmask(int level) { return level == 2 ? 0x3FFu : 0x7FFu; }
+__host__ __device__ constexpr uint32_t level_pmask(int level) { return level == 0 ? 0u : (level == 1 ? 0xFFE00000u : 0xFFFFFC00u); }
 
 __device__ __forceinline__ uint32_t order_key(float v) {
     uint32_t b = __float_as_uint(v);
@@ -38,92 +66,105 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
-__global__ void select_init_kernel(SelectState *st, long long r0, long long r1) {
-    for (int i = threadIdx.x; i < 2 * kDigits; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
-    if (threadIdx.x == 0) { st->prefix[0] = st->prefix[1] = 0u; st->done = 0u; st->rank[0] = r0; st->rank[1] = r1; }
+// index arithmetic of _Quantile_T (sort.cu:13-19): int64 * float -> float, __float2int_rn (half-even, saturating), CLIP<int>(pos, 0, n - 1)
+__device__ __forceinline__ long long quantile_rank(int64_t n, float frac) {
+    int pos = __float2int_rn((float)n * frac);
+    const int last = (int)(n - 1);
+    pos = pos > last ? last : pos;
+    return pos < 0 ? 0 : pos;
 }
 
-// Block-wide prefix sum over the digit histogram of each rank (kDigits / TPB consecutive digits per thread, warp shuffles): pick the digit
-// bucket that contains the rank, extend the prefix, clear the histograms for the next pass.  Run by the LAST CTA of a pass to finish its flush.
-template <int PASS, int TPB>
-__device__ __noinline__ void select_scan(SelectState *st, float *out, int out_stride) {
-    constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
-    constexpr int D = kDigits / TPB;                                    // digits per thread: 2 (1024 threads) or 8 (256 threads)
+// one CTA per tensor.  q_mode: ranks = {rn(n q), rn(n (1 - q))};  otherwise explicit ranks (isotone)
+__global__ void select_init_kernel(SelectState *states, const ppq_b200_tensor_desc *descs, int64_t n_single, float q, int q_mode,
+                                   long long r0, long long r1) {
+    SelectState *st = states + blockIdx.x;
+    for (int i = threadIdx.x; i < 2 * kDigits; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
+    if (threadIdx.x == 0) {
+        const int64_t n = descs ? descs[blockIdx.x].n : n_single;
+        if (q_mode) { r0 = quantile_rank(n, q); r1 = quantile_rank(n, 1.0f - q); }
+        st->prefix[0] = st->prefix[1] = 0u; st->mode[0] = st->mode[1] = kModeHist; st->shared = 1u; st->done = 0u;
+        st->ccount[0] = st->ccount[1] = 0u; st->cbuf[0] = 0u; st->cbuf[1] = 1u; st->clevel[0] = st->clevel[1] = 0u;
+        st->compacted[0] = st->compacted[1] = 0u; st->kmin[0] = st->kmin[1] = 0xFFFFFFFFu; st->kmax[0] = st->kmax[1] = 0u;
+        st->rank[0] = r0; st->rank[1] = r1; st->count[0] = st->count[1] = n;
+    }
+}
+
+// Block-wide search of the bucket that contains rank k in a 2048-bin histogram (TPB threads, kDigits / TPB consecutive bins per thread, warp
+// shuffles).  Exactly one (thread, bin) matches because k < total.  Results through shared memory; ends with a barrier.
+template <int TPB, class Load>
+__device__ __forceinline__ void block_pick(Load &&load, unsigned long long k, unsigned int *digit, unsigned long long *before_out, unsigned long long *cnt_out) {
+    constexpr int D = kDigits / TPB;
     __shared__ unsigned long long warp_tot[TPB / 32];
-    __shared__ unsigned int new_prefix[2];
-    __shared__ long long new_rank[2];
-    const bool same = st->prefix[0] == st->prefix[1];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    unsigned long long c[D], mine = 0;
+#pragma unroll
+    for (int j = 0; j < D; j++) { c[j] = load(D * t + j); mine += c[j]; }
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+    __syncthreads();                                                   // warp_tot may still be read by a previous call
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    unsigned long long before = incl - mine;
+    for (int i = 0; i < w; i++) before += warp_tot[i];
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        if (k >= before && k < before + c[j]) { *digit = (unsigned int)(D * t + j); *before_out = before; *cnt_out = c[j]; }
+        before += c[j];
+    }
+    __syncthreads();
+}
+
+// Resolve a pass for one tensor: run by the last CTA of the pass (single tensor) or by select_scan_kernel (tables).
+template <int LEVEL, int TPB>
+__device__ __noinline__ void select_scan(SelectState *st, long long cap) {
+    __shared__ unsigned int s_digit;
+    __shared__ unsigned long long s_before, s_cnt;
+    const int t = threadIdx.x;
+    const bool shared_in = st->shared != 0;
     for (int r = 0; r < 2; r++) {
-        const unsigned long long *h = st->hist[(r == 1 && same) ? 0 : r];
-        const unsigned long long k = (unsigned long long)st->rank[r];
-        unsigned long long c[D], mine = 0;
-#pragma unroll
-        for (int j = 0; j < D; j++) { c[j] = __ldcg(h + D * t + j); mine += c[j]; }        // written by other CTAs' atomics: read at L2
-        unsigned long long incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
-        if (lane == 31) warp_tot[w] = incl;
-        __syncthreads();
-        unsigned long long before = incl - mine;
-        for (int i = 0; i < w; i++) before += warp_tot[i];
-        // the bucket d with  before(d) <= k < before(d) + count(d); ranks are always < total, so exactly one (thread, digit) matches
-#pragma unroll
-        for (int j = 0; j < D; j++) {
-            if (k >= before && k < before + c[j]) { new_prefix[r] = st->prefix[r] | ((unsigned int)(D * t + j) << shift); new_rank[r] = (long long)(k - before); }
-            before += c[j];
+        const int src = (r == 1 && shared_in) ? 0 : r;
+        const unsigned int mode = st->mode[r];                          // uniform
+        if (mode == kModeDone) continue;
+        if (mode == kModeCompact) { if (t == 0) st->compacted[r] = 1u; continue; }
+        const unsigned int kmin = __ldcg(&st->kmin[src]), kmax = __ldcg(&st->kmax[src]);
+        if (LEVEL > 0 && kmin == kmax) {                               // the whole bucket is one repeated value
+            __syncthreads();
+            if (t == 0) { st->prefix[r] = kmin; st->mode[r] = kModeDone; }
+            continue;
+        }
+        // other CTAs' atomics wrote the histogram: read it at L2
+        const unsigned long long *h = st->hist[src];
+        block_pick<TPB>([&](int i) { return __ldcg(h + i); }, (unsigned long long)st->rank[r], &s_digit, &s_before, &s_cnt);
+        if (t == 0) {
+            st->prefix[r] |= s_digit << level_shift(LEVEL);
+            st->rank[r] -= (long long)s_before;
+            st->count[r] = (long long)s_cnt;
+            if (LEVEL == 2) st->mode[r] = kModeDone;
+            else if ((long long)s_cnt <= cap) { st->mode[r] = kModeCompact; st->clevel[r] = LEVEL + 1; }
         }
         __syncthreads();
     }
     for (int i = t; i < 2 * kDigits; i += TPB) (&st->hist[0][0])[i] = 0ull;
-    if (t < 2) {
-        st->prefix[t] = new_prefix[t];
-        st->rank[t] = new_rank[t];
-        if (PASS == 2) out[t * out_stride] = key_to_float(new_prefix[t]);
+    if (t == 0) {
+        const bool same = st->prefix[0] == st->prefix[1] && st->mode[0] == st->mode[1] && st->mode[0] != kModeDone;
+        st->shared = same ? 1u : 0u;
+        if (st->mode[0] == kModeCompact && !st->compacted[0]) st->cbuf[0] = 0u;
+        if (st->mode[1] == kModeCompact && !st->compacted[1]) st->cbuf[1] = same ? 0u : 1u;
+        st->kmin[0] = st->kmin[1] = 0xFFFFFFFFu; st->kmax[0] = st->kmax[1] = 0u;
+        st->done = 0u;
     }
-    if (t == 0) st->done = 0u;
 }
 
-// PASS 0: digit = key[31:21];  PASS 1: key[20:10] among keys whose top 11 bits match;  PASS 2: key[9:0] among top-22 matches.
-// Pass 0 is a histogram of every element (unconditional shared red, as in collectors.cu): two 1024-thread CTAs per SM, grid-stride.
-// In passes 1 and 2 only the elements of the one or two buckets chosen so far count: a vector whose four elements all miss both prefixes
-// -- the common case, the requested ranks sit in the tails -- costs one AND + three compares per element and no shared-memory traffic,
-// so these passes use the launch shape of the min/max collector: 256-thread CTAs, 8 per SM, every warp walking contiguous 2 KB segments.
-template <int PASS, int TPB>
-__global__ void __launch_bounds__(TPB, PASS == 0 ? 2 : 6)            // 32 / 40 registers; the scan of the last CTA may spill, it runs once
-select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restrict__ st, float *out, int out_stride) {
-    __shared__ int sh[2][kDigits];
-    __shared__ bool is_last;
-    for (int i = threadIdx.x; i < 2 * kDigits; i += TPB) (&sh[0][0])[i] = 0;
-    __syncthreads();
-    constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
-    constexpr uint32_t dmask = PASS == 2 ? 0x3FFu : 0x7FFu;
-    constexpr uint32_t pmask = PASS == 0 ? 0u : (PASS == 1 ? 0xFFE00000u : 0xFFFFFC00u);
-    const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
-    const bool same = (p0 == p1);
-    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(&sh[0][0]), a1 = (uint32_t)__cvta_generic_to_shared(&sh[1][0]);
-    auto count = [&](uint32_t k) {
-        const uint32_t hi = k & pmask, d = (k >> shift) & dmask;
-        if (PASS == 0) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + d * 4u) : "memory"); return; }
-        if (hi == p0) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + d * 4u) : "memory");
-        if (!same && hi == p1) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1 + d * 4u) : "memory");
-    };
-    // Fast rejection on the RAW bits (passes 1-2): key & pmask == p  <=>  bits & pmask == raw(p), because the key transform only depends on
-    // the sign, which the prefix fixes.  -0.0 is the one exception (its key is +0's): when a prefix is the bucket of +0 the raw pattern of
-    // -0.0 is accepted too; a false positive only costs the exact test in count().  One AND + three compares per element.
-    auto raw_of = [&](uint32_t p) { return (p & 0x80000000u) ? (p & 0x7FFFFFFFu) : (~p & pmask); };
-    const uint32_t c0 = raw_of(p0), c1 = raw_of(p1), c2 = (p0 == 0x80000000u || p1 == 0x80000000u) ? 0x80000000u : c0;
-    auto hit = [&](float f) { const uint32_t t = __float_as_uint(f) & pmask; return (t == c0) | (t == c1) | (t == c2); };
-    auto visit4 = [&](const float4 &v) {
-        if (PASS != 0 && !(hit(v.x) | hit(v.y) | hit(v.z) | hit(v.w))) return;
-        count(order_key(v.x)); count(order_key(v.y)); count(order_key(v.z)); count(order_key(v.w));
-    };
-    const int64_t first = (int64_t)blockIdx.x * TPB + threadIdx.x, stride = (int64_t)gridDim.x * TPB;
-    if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+// Streams elements [a, b) of x (a multiple of 4 when x is 16-byte aligned) through `visit4` / `visit1`.
+template <int U, bool SEGMENTS, class F4, class F1>
+__device__ __forceinline__ void stream_range(const float *__restrict__ x, int64_t a, int64_t b, int64_t first, int64_t stride, F4 &&visit4, F1 &&visit1) {
+    const float *p = x + a;
+    const int64_t n = b - a;
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
         const int64_t n4 = n >> 2;
-        const float4 *x4 = reinterpret_cast<const float4 *>(x);
-        constexpr int U = 4;
-        if (PASS == 0) {
+        const float4 *x4 = reinterpret_cast<const float4 *>(p);
+        if (!SEGMENTS) {
             for (int64_t i = first; i < n4; i += U * stride) {
                 float4 v[U];
 #pragma unroll
@@ -131,9 +172,8 @@ select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restri
 #pragma unroll
                 for (int j = 0; j < U; j++) if (i + j * stride < n4) visit4(v[j]);
             }
-        } else {
-            // warp-contiguous segments of 32 lanes x U vectors (2 KB)
-            const int64_t lane = threadIdx.x & 31, warps = stride >> 5;
+        } else {                                                       // warp-contiguous segments of 32 lanes x U vectors (2 KB)
+            const int64_t lane = first & 31, warps = stride >> 5;
             for (int64_t sg = first >> 5; sg * (32 * U) < n4; sg += warps) {
                 const int64_t base = sg * (32 * U) + lane;
                 float4 v[U];
@@ -144,40 +184,204 @@ select_hist_kernel(const float *__restrict__ x, int64_t n, SelectState *__restri
             }
         }
         const int64_t t = (n4 << 2) + first;
-        if (t < n) count(order_key(x[t]));
+        if (t < n) visit1(p[t]);
     } else {
-        for (int64_t i = first; i < n; i += stride) count(order_key(ld_stream1(x + i)));
+        for (int64_t i = first; i < n; i += stride) visit1(ld_stream1(p + i));
     }
+}
+
+// One pass over the part [a, b) of a tensor for the CTA (`first`, `stride` in threads of the cooperating group).  Returns false when the
+// tensor needs nothing at this level (uniform over the grid).
+template <int LEVEL, int TPB>
+__device__ __forceinline__ bool select_pass(const float *__restrict__ x, int64_t a, int64_t b, int64_t first, int64_t stride,
+                                            SelectState *__restrict__ st, uint32_t *__restrict__ bufs, int64_t cap, int (*sh)[kDigits], unsigned int *sh_cnt) {
+    constexpr int shift = level_shift(LEVEL);
+    constexpr uint32_t dmask = level_dmask(LEVEL), pmask = level_pmask(LEVEL);
+    const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
+    const unsigned m0 = st->mode[0], m1 = st->mode[1];
+    const bool same = st->shared != 0;
+    const bool need0 = LEVEL == 0 || m0 == kModeHist || (m0 == kModeCompact && !st->compacted[0]);
+    const bool need1 = LEVEL > 0 && !same && (m1 == kModeHist || (m1 == kModeCompact && !st->compacted[1]));
+    if (!need0 && !need1) return false;
+    for (int i = threadIdx.x; i < 2 * kDigits; i += TPB) (&sh[0][0])[i] = 0;
+    if (threadIdx.x < 2) sh_cnt[threadIdx.x] = 0u;
     __syncthreads();
-    for (int i = threadIdx.x; i < kDigits; i += TPB) {
-        if (sh[0][i]) atomicAdd(&st->hist[0][i], (unsigned long long)sh[0][i]);
-        if (!same && sh[1][i]) atomicAdd(&st->hist[1][i], (unsigned long long)sh[1][i]);
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(&sh[0][0]), a1 = (uint32_t)__cvta_generic_to_shared(&sh[1][0]);
+    uint32_t *buf0 = bufs, *buf1 = bufs + cap;
+    uint32_t kmin0 = 0xFFFFFFFFu, kmax0 = 0u, kmin1 = 0xFFFFFFFFu, kmax1 = 0u;
+    auto take = [&](uint32_t k, int r, unsigned mode, uint32_t sa, uint32_t *gbuf, uint32_t &kmin, uint32_t &kmax) {
+        if (mode == kModeHist) {
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(sa + ((k >> shift) & dmask) * 4u) : "memory");
+            kmin = min(kmin, k); kmax = max(kmax, k);
+        } else {                                                        // compact: stage in shared memory, spill straight to the workspace when full
+            const unsigned idx = atomicAdd(&sh_cnt[r], 1u);
+            if (idx < (unsigned)kStage) sh[r][idx] = (int)k;
+            else { const unsigned g = atomicAdd(&st->ccount[r], 1u); if ((long long)g < cap) gbuf[g] = k; }
+        }
+    };
+    auto count = [&](uint32_t k) {
+        if (LEVEL == 0) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + ((k >> shift) & dmask) * 4u) : "memory"); return; }
+        const uint32_t hi = k & pmask;
+        if (need0 && hi == p0) take(k, 0, m0, a0, buf0, kmin0, kmax0);
+        if (need1 && hi == p1) take(k, 1, m1, a1, buf1, kmin1, kmax1);
+    };
+    // Fast rejection on the RAW bits (levels 1-2): key & pmask == p  <=>  bits & pmask == raw(p), because the key transform only depends on
+    // the sign, which the prefix fixes.  -0.0 is the one exception (its key is +0's): when a prefix is the bucket of +0 the raw pattern of
+    // -0.0 is accepted too; a false positive only costs the exact test in count().  One AND + three compares per element.
+    auto raw_of = [&](uint32_t p) { return (p & 0x80000000u) ? (p & 0x7FFFFFFFu) : (~p & pmask); };
+    const uint32_t zero_bucket = 0x80000000u & pmask;                   // the bucket of +0 at this level
+    const uint32_t c0 = raw_of(p0), c1 = raw_of(p1), c2 = (p0 == zero_bucket || p1 == zero_bucket) ? 0x80000000u : c0;
+    auto hit = [&](float f) { const uint32_t t = __float_as_uint(f) & pmask; return (t == c0) | (t == c1) | (t == c2); };
+    auto visit4 = [&](const float4 &v) {
+        if (LEVEL != 0 && !(hit(v.x) | hit(v.y) | hit(v.z) | hit(v.w))) return;
+        count(order_key(v.x)); count(order_key(v.y)); count(order_key(v.z)); count(order_key(v.w));
+    };
+    auto visit1 = [&](float f) { count(order_key(f)); };
+    stream_range<4, LEVEL != 0>(x, a, b, first, stride, visit4, visit1);
+    __syncthreads();
+    // flush: histograms with global atomics on the non-empty digits, staged keys after one reservation per CTA and rank
+    __shared__ unsigned int s_base[2];
+    for (int r = 0; r < 2; r++) {
+        const bool need = r == 0 ? need0 : need1;
+        const unsigned mode = r == 0 ? m0 : m1;
+        if (!need) continue;
+        if (LEVEL == 0 || mode == kModeHist) {
+            for (int i = threadIdx.x; i < kDigits; i += TPB) if (sh[r][i]) atomicAdd(&st->hist[r][i], (unsigned long long)sh[r][i]);
+            if (LEVEL > 0) {
+                uint32_t lo = r == 0 ? kmin0 : kmin1, hi = r == 0 ? kmax0 : kmax1;
+                lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+                if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&st->kmin[r], lo); atomicMax(&st->kmax[r], hi); }
+            }
+        } else {
+            const unsigned m = min(sh_cnt[r], (unsigned)kStage);
+            if (threadIdx.x == 0 && m) s_base[r] = atomicAdd(&st->ccount[r], m);
+            __syncthreads();
+            uint32_t *gbuf = r == 0 ? buf0 : buf1;
+            for (unsigned i = threadIdx.x; i < m; i += TPB) if ((long long)(s_base[r] + i) < cap) gbuf[s_base[r] + i] = (uint32_t)sh[r][i];
+        }
     }
-    // the last CTA to get here resolves the pass (no separate scan launch): every CTA's atomics are ordered before its ticket
+    return true;
+}
+
+// ---- single tensor: the whole grid interleaves over the tensor, the last CTA to finish resolves the pass ------------------------------
+template <int LEVEL, int TPB>
+__global__ void __launch_bounds__(TPB, LEVEL == 0 ? 2 : 6)
+select_pass_kernel(const float *__restrict__ x, int64_t n, SelectState *__restrict__ st, uint32_t *__restrict__ bufs, int64_t cap) {
+    __shared__ int sh[2][kDigits];
+    __shared__ unsigned int sh_cnt[2];
+    __shared__ bool is_last;
+    if (!select_pass<LEVEL, TPB>(x, 0, n, (int64_t)blockIdx.x * TPB + threadIdx.x, (int64_t)gridDim.x * TPB, st, bufs, cap, sh, sh_cnt)) return;
+    // every CTA's atomics are ordered before its ticket
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(&st->done, 1u) == gridDim.x - 1);
     __syncthreads();
     if (is_last) {
         __threadfence();
-        select_scan<PASS, TPB>(st, out, out_stride);
+        select_scan<LEVEL, TPB>(st, cap);
     }
 }
 
-constexpr int kFilterThreads = 256;
+// ---- tables: each CTA owns one contiguous span of the concatenation of all tensors; a separate one-CTA-per-tensor launch resolves the pass
+template <int LEVEL, int TPB>
+__global__ void __launch_bounds__(TPB, LEVEL == 0 ? 2 : 6)
+multi_select_pass_kernel(const ppq_b200_tensor_desc *__restrict__ descs, int count, SelectState *__restrict__ states,
+                         uint32_t *__restrict__ bufs, int64_t cap) {
+    __shared__ int sh[2][kDigits];
+    __shared__ unsigned int sh_cnt[2];
+    extern __shared__ long long prefix[];                              // [count + 1]
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        for (int t = 0; t < count; t++) { prefix[t] = run; run += descs[t].n; }
+        prefix[count] = run;
+    }
+    __syncthreads();
+    const int64_t total = prefix[count];
+    int64_t span = (total + gridDim.x - 1) / gridDim.x;
+    span = (span + 3) & ~(int64_t)3;
+    const int64_t s0 = (int64_t)blockIdx.x * span, s1 = (s0 + span) < total ? (s0 + span) : total;
+    if (s0 >= total) return;
+    int t = 0;
+    { int lo = 0, hi = count - 1; while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (prefix[mid] <= s0) lo = mid; else hi = mid - 1; } t = lo; }
+    for (; t < count && prefix[t] < s1; t++) {
+        const ppq_b200_tensor_desc d = descs[t];
+        int64_t a = s0 - prefix[t]; if (a < 0) a = 0;
+        int64_t b = s1 - prefix[t]; if (b > d.n) b = d.n;
+        a = (a + 3) & ~(int64_t)3; if (a > d.n) a = d.n;               // both neighbours round the shared boundary the same way
+        if (b < d.n) b = (b + 3) & ~(int64_t)3; if (b > d.n) b = d.n;
+        if (b <= a) continue;                                          // uniform per CTA
+        select_pass<LEVEL, TPB>(d.x, a, b, threadIdx.x, TPB, states + t, bufs + (int64_t)t * 2 * cap, cap, sh, sh_cnt);
+        __syncthreads();
+    }
+}
 
-static int select_two(const float *x, int64_t n, long long r0, long long r1, float *out, int out_stride, SelectState *st, cudaStream_t s) {
-    // pass 0 needs 32 registers per thread: two 1024-thread CTAs fit on an SM
-    int64_t g0 = (n + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
-    if (g0 > 2 * kSMs) g0 = 2 * kSMs;
-    if (g0 < 1) g0 = 1;
+template <int LEVEL>
+__global__ void __launch_bounds__(kSelThreads)
+select_scan_kernel(SelectState *states, int64_t cap) {
+    SelectState *st = states + blockIdx.x;
+    if (LEVEL > 0) {                                                   // nothing was streamed for this tensor at this level
+        const unsigned m0 = st->mode[0], m1 = st->mode[1];
+        const bool need0 = m0 == kModeHist || (m0 == kModeCompact && !st->compacted[0]);
+        const bool need1 = !st->shared && (m1 == kModeHist || (m1 == kModeCompact && !st->compacted[1]));
+        if (!need0 && !need1) return;
+    }
+    select_scan<LEVEL, kSelThreads>(st, cap);
+}
+
+// ---- finish: one CTA per (tensor, rank) selects among the compacted keys (or just reports a resolved key) -------------------------------
+__global__ void __launch_bounds__(kSelThreads)
+select_finish_kernel(const SelectState *__restrict__ states, const uint32_t *__restrict__ bufs, int64_t cap,
+                     const ppq_b200_tensor_desc *__restrict__ descs, float *__restrict__ out, int64_t out_stride) {
+    __shared__ int sh[kDigits];
+    __shared__ unsigned int s_digit;
+    __shared__ unsigned long long s_before, s_cnt;
+    const int tensor = blockIdx.x >> 1, r = blockIdx.x & 1;
+    const SelectState *st = states + tensor;
+    float *dst = out + (descs ? (int64_t)descs[tensor].slot : 0) * out_stride + r;
+    unsigned int key = st->prefix[r];
+    if (st->mode[r] == kModeCompact) {
+        const uint32_t *keys = bufs + ((int64_t)tensor * 2 + st->cbuf[r]) * cap;
+        const unsigned m = st->ccount[st->cbuf[r]];
+        unsigned long long k = (unsigned long long)st->rank[r];
+        for (int level = (int)st->clevel[r]; level <= 2; level++) {
+            const int shift = level_shift(level);
+            const uint32_t dmask = level_dmask(level), pmask = level_pmask(level);
+            for (int i = threadIdx.x; i < kDigits; i += kSelThreads) sh[i] = 0;
+            __syncthreads();
+            for (unsigned i = threadIdx.x; i < m; i += kSelThreads) {
+                const uint32_t v = __ldcg(keys + i);
+                if ((v & pmask) == (key & pmask)) atomicAdd(&sh[(v >> shift) & dmask], 1);
+            }
+            __syncthreads();
+            block_pick<kSelThreads>([&](int i) { return (unsigned long long)sh[i]; }, k, &s_digit, &s_before, &s_cnt);
+            key |= s_digit << shift;
+            k -= s_before;
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) *dst = key_to_float(key);
+}
+
+static inline int grid_pass0(int64_t n) {
+    int64_t g = (n + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
+    if (g > 2 * sm_count()) g = 2 * sm_count();                                       // pass 0 needs 32 registers per thread: two 1024-thread CTAs fit on an SM
+    return (int)(g < 1 ? 1 : g);
+}
+static inline int grid_filter(int64_t n) {
     int64_t g = (n + (int64_t)kFilterThreads * 16 - 1) / ((int64_t)kFilterThreads * 16);
-    if (g > 6 * kSMs) g = 6 * kSMs;                                       // 40 registers, 17.5 KB of smem: six CTAs per SM, one wave
-    if (g < 1) g = 1;
-    select_init_kernel<<<1, 1024, 0, s>>>(st, r0, r1);
-    select_hist_kernel<0, kSelThreads><<<(int)g0, kSelThreads, 0, s>>>(x, n, st, out, out_stride);
-    select_hist_kernel<1, kFilterThreads><<<(int)g, kFilterThreads, 0, s>>>(x, n, st, out, out_stride);
-    select_hist_kernel<2, kFilterThreads><<<(int)g, kFilterThreads, 0, s>>>(x, n, st, out, out_stride);
+    if (g > 6 * sm_count()) g = 6 * sm_count();                                       // 40 registers, 16.5 KB of smem: six CTAs per SM, one wave
+    return (int)(g < 1 ? 1 : g);
+}
+
+static int select_two(const float *x, int64_t n, int q_mode, float q, long long r0, long long r1, float *out, void *workspace, cudaStream_t s) {
+    SelectState *st = (SelectState *)workspace;
+    uint32_t *bufs = (uint32_t *)(st + 1);
+    const int64_t cap = kDefaultCap;
+    select_init_kernel<<<1, 1024, 0, s>>>(st, nullptr, n, q, q_mode, r0, r1);
+    select_pass_kernel<0, kSelThreads><<<grid_pass0(n), kSelThreads, 0, s>>>(x, n, st, bufs, cap);
+    select_pass_kernel<1, kFilterThreads><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
+    select_pass_kernel<2, kFilterThreads><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
+    select_finish_kernel<<<2, kSelThreads, 0, s>>>(st, bufs, cap, nullptr, out, 0);
     return (int)cudaGetLastError();
 }
 
@@ -187,39 +391,50 @@ using namespace ppqb;
 
 extern "C" {
 
-int64_t ppq_b200_quantile_workspace_bytes(void) { return (int64_t)sizeof(SelectState); }
+int64_t ppq_b200_quantile_workspace_bytes(void) { return (int64_t)sizeof(SelectState) + 2 * kDefaultCap * (int64_t)sizeof(uint32_t); }
+
+int64_t ppq_b200_multi_quantile_workspace_bytes(int count, int64_t cap) {
+    if (count <= 0 || cap <= 0) return 0;
+    return (int64_t)count * ((int64_t)sizeof(SelectState) + 2 * cap * (int64_t)sizeof(uint32_t));
+}
 
 int ppq_b200_quantile_t(const float *x, int64_t n, float q, float *out2, void *workspace, void *stream) {
     if (n <= 0 || !x || !out2 || !workspace) return (int)cudaErrorInvalidValue;
-    // index arithmetic of _Quantile_T (sort.cu:13-19): int64 * float -> float, __float2int_rn (half-even, saturating), CLIP
-    const float fa = (float)n * q;
-    const float fb = (float)n * (1.0f - q);
-    auto rn = [](float v) -> long long {
-        if (v != v) return 0;
-        if (v >= 2147483648.0f) return 2147483647LL;
-        if (v <= -2147483648.0f) return -2147483648LL;
-        return (long long)__builtin_nearbyintf(v);
-    };
-    long long a = rn(fa), b = rn(fb);
-    // the reference clips with CLIP<int>(pos, 0, n - 1) where n - 1 is converted to int
-    const long long last = (long long)(int)(n - 1);
-    a = a > last ? last : (a < 0 ? 0 : a);
-    b = b > last ? last : (b < 0 ? 0 : b);
-    return select_two(x, n, a, b, out2, 1, (SelectState *)workspace, (cudaStream_t)stream);
+    return select_two(x, n, 1, q, 0, 0, out2, workspace, (cudaStream_t)stream);
+}
+
+int ppq_b200_multi_quantile_t(const ppq_b200_tensor_desc *descs, int count, int64_t max_n, float q, float *out, int64_t out_stride,
+                              void *workspace, int64_t cap, void *stream) {
+    if (count <= 0 || max_n <= 0 || !descs || !out || !workspace || cap <= 0 || out_stride < 2) return (int)cudaErrorInvalidValue;
+    const size_t smem = (size_t)(count + 1) * sizeof(long long);
+    if (smem > 24 * 1024) return (int)cudaErrorInvalidValue;
+    cudaStream_t s = (cudaStream_t)stream;
+    SelectState *states = (SelectState *)workspace;
+    uint32_t *bufs = (uint32_t *)(states + count);
+    int64_t work = (int64_t)count * max_n;
+    int g0 = grid_pass0(work), g1 = grid_filter(work);
+    select_init_kernel<<<count, 1024, 0, s>>>(states, descs, 0, q, 1, 0, 0);
+    multi_select_pass_kernel<0, kSelThreads><<<g0, kSelThreads, smem, s>>>(descs, count, states, bufs, cap);
+    select_scan_kernel<0><<<count, kSelThreads, 0, s>>>(states, cap);
+    multi_select_pass_kernel<1, kFilterThreads><<<g1, kFilterThreads, smem, s>>>(descs, count, states, bufs, cap);
+    select_scan_kernel<1><<<count, kSelThreads, 0, s>>>(states, cap);
+    multi_select_pass_kernel<2, kFilterThreads><<<g1, kFilterThreads, smem, s>>>(descs, count, states, bufs, cap);
+    select_scan_kernel<2><<<count, kSelThreads, 0, s>>>(states, cap);
+    select_finish_kernel<<<2 * count, kSelThreads, 0, s>>>(states, bufs, cap, descs, out, out_stride);
+    return (int)cudaGetLastError();
 }
 
 int ppq_b200_isotone_t(const float *x, int64_t n, float *out4, void *workspace, void *stream) {
     if (n <= 0 || !x || !out4 || !workspace) return (int)cudaErrorInvalidValue;
-    SelectState *st = (SelectState *)workspace;
     if (n == 1) {
-        int rc = select_two(x, n, 0, 0, out4, 1, st, (cudaStream_t)stream);
+        int rc = select_two(x, n, 0, 0.f, 0, 0, out4, workspace, (cudaStream_t)stream);
         if (rc) return rc;
-        return select_two(x, n, 0, 0, out4 + 2, 1, st, (cudaStream_t)stream);
+        return select_two(x, n, 0, 0.f, 0, 0, out4 + 2, workspace, (cudaStream_t)stream);
     }
     // out = { sorted[n-1], sorted[n-2], sorted[0], sorted[1] }
-    int rc = select_two(x, n, n - 1, n - 2, out4, 1, st, (cudaStream_t)stream);
+    int rc = select_two(x, n, 0, 0.f, n - 1, n - 2, out4, workspace, (cudaStream_t)stream);
     if (rc) return rc;
-    return select_two(x, n, 0, 1, out4 + 2, 1, st, (cudaStream_t)stream);
+    return select_two(x, n, 0, 0.f, 0, 1, out4 + 2, workspace, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -229,6 +229,20 @@ void Multi_Histogram_T(const Tensor &descs, const int64_t max_numel, const Tenso
                                            max_numel, F(hist_scale_arena), clip_outliers, hist_arena.data_ptr<int>(), bins, Stream()),
                 "Multi_Histogram_T");
 }
+// out: float tensor, tensor i writes out.flat[slot_i * out_stride + {0, 1}] = {upper, lower} quantile; workspace: uint8 scratch
+void Multi_Quantile_T(const Tensor &descs, const int64_t max_numel, const float q, Tensor &out, const int64_t out_stride, Tensor &workspace,
+                      const int64_t cap) {
+    CheckTensor(descs, at::kLong, "Descriptors(Expect to be INT64)");
+    CheckTensor(out, at::kFloat, "Quantiles(Expect to be FP32)");
+    if (descs.dim() != 2 || descs.size(1) != 3 || !descs.is_contiguous()) throw KernelFailure("Kernel Failure, descriptor table must be [count, 3] int64.");
+    const int count = (int)descs.size(0);
+    if (workspace.scalar_type() != at::kByte || workspace.numel() < ppq_b200_multi_quantile_workspace_bytes(count, cap))
+        throw KernelFailure("Kernel Failure, quantile workspace is too small (see Multi_Quantile_Workspace_Bytes).");
+    const c10::cuda::CUDAGuard guard(descs.device());
+    CheckStatus(ppq_b200_multi_quantile_t(reinterpret_cast<const ppq_b200_tensor_desc *>(descs.data_ptr<int64_t>()), count, max_numel, q,
+                                          out.data_ptr<float>(), out_stride, workspace.data_ptr(), cap, Stream()), "Multi_Quantile_T");
+}
+int64_t Multi_Quantile_Workspace_Bytes(const int count, const int64_t cap) { return ppq_b200_multi_quantile_workspace_bytes(count, cap); }
 std::vector<Tensor> MinMax_To_Scale_Offset(const Tensor &mins, const Tensor &maxs, const int64_t stride, const int quant_min,
                                            const int quant_max, const bool symmetrical, const bool power_of_2, const double min_scale) {
     CheckTensor(mins, at::kFloat, "Min(Expect to be FP32)");
@@ -311,6 +325,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("Histogram_T_DeviceScale", Histogram_T_DeviceScale, "Histogram_T_DeviceScale");
     m.def("Multi_MinMax_T", Multi_MinMax_T, "Multi_MinMax_T");
     m.def("Multi_Histogram_T", Multi_Histogram_T, "Multi_Histogram_T");
+    m.def("Multi_Quantile_T", Multi_Quantile_T, "Multi_Quantile_T");
+    m.def("Multi_Quantile_Workspace_Bytes", Multi_Quantile_Workspace_Bytes, "Multi_Quantile_Workspace_Bytes");
     m.def("MinMax_To_Scale_Offset", MinMax_To_Scale_Offset, "MinMax_To_Scale_Offset");
     m.def("Hist_Scale_From_MinMax", Hist_Scale_From_MinMax, "Hist_Scale_From_MinMax");
     m.def("KL_Search", KL_Search, "KL_Search");

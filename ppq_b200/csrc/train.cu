@@ -170,8 +170,8 @@ static inline Channel make_channel(int64_t n, int64_t epc, int C) {
     return ch;
 }
 static inline bool geom_ok(int64_t n, int64_t epc, int C) { return n > 0 && n <= 0x7fffffffLL && epc > 0 && C > 0 && n % epc == 0; }
-static inline int flat_grid(int64_t n) { int64_t g = (n + kTThreads * 8 - 1) / (kTThreads * 8); return (int)(g > kSMs * 8 ? kSMs * 8 : (g < 1 ? 1 : g)); }
-static inline int row_grid(int64_t rows) { return (int)(rows > kSMs * 8 ? kSMs * 8 : rows); }
+static inline int flat_grid(int64_t n) { int64_t g = (n + kTThreads * 8 - 1) / (kTThreads * 8); return (int)(g > sm_count() * 8 ? sm_count() * 8 : (g < 1 ? 1 : g)); }
+static inline int row_grid(int64_t rows) { return (int)(rows > sm_count() * 8 ? sm_count() * 8 : rows); }
 
 }  // namespace ppqb
 

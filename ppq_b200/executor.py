@@ -56,6 +56,15 @@ _KINDS = {torch.nn.Conv2d: 'Conv', torch.nn.ConvTranspose2d: 'ConvTranspose', to
           torch.nn.ReLU6: 'Clip', torch.nn.MaxPool2d: 'MaxPool', torch.nn.AdaptiveAvgPool2d: 'GlobalAveragePool',
           torch.nn.AvgPool2d: 'AveragePool', torch.nn.Flatten: 'Flatten', torch.nn.Sigmoid: 'Sigmoid', torch.nn.GELU: 'Gelu',
           torch.nn.Hardswish: 'HardSwish', torch.nn.Softmax: 'Softmax', torch.nn.LeakyReLU: 'LeakyRelu', Add: 'Add', Concat: 'Concat'}
+
+
+def kind_of(module: torch.nn.Module) -> Optional[str]:
+    """The reference operator type a module stands for (exact type first, then base classes, so that a subclass of nn.Linear is a Gemm)."""
+    for t in type(module).__mro__:
+        if t in _KINDS: return _KINDS[t]
+    return None
+
+
 COMPUTING_OP = {'Conv', 'Gemm', 'ConvTranspose', 'MatMul'}                              # core/common.py:55
 # core/common.py:51-53 -- as written upstream, where a missing comma makes 'Dropout' 'Slice' one string: neither is passive
 PASSIVE_OPERATIONS = {'MaxPool', 'GlobalMaxPool', 'Reshape', 'Flatten', 'Identity', 'DropoutSlice', 'Pad', 'Split', 'Transpose',
@@ -124,7 +133,7 @@ class TorchExecutor:
         self._produced = {}                                            # id(tensor) -> (operation, tensor, version at production)
         self._quant_fn = PPQuantFunction
         for m in self.model.modules():
-            if type(m) in _KINDS:
+            if kind_of(m) is not None:
                 m.register_forward_pre_hook(self._pre)
                 m.register_forward_hook(self._post)
         with torch.no_grad():
@@ -221,7 +230,7 @@ class TorchExecutor:
         idx = self._calls.get(id(module), 0)
         name = f'{self._names[id(module)]}#{idx}'
         if self._tracing and name not in self.operations:
-            self.operations[name] = QuantableOperation(name, module, _KINDS[type(module)], num_inputs)
+            self.operations[name] = QuantableOperation(name, module, kind_of(module), num_inputs)
             self._order.append(name)
         return self.operations[name]
 
@@ -424,6 +433,7 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
     for c in cfgs: c.observer_algorithm = method
     if iter(batches) is batches: batches = list(batches)                  # a one-shot iterator would leave phase 2 without data
     dev = next(executor.model.parameters()).device
+    if graphs and method == 'percentile': raise ValueError('graphs=True needs static statistics buffers; the percentile observer keeps one row per batch')
     cal = ArenaCalibrator(len(cfgs), dev, method=method, group=group)
     static_in = None
     mutated = None                                                        # slots whose tensors are overwritten later in the forward
@@ -431,6 +441,7 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
         graph = None
         overlapped = prefetch and to_device is not None and not graphs and dev.type == 'cuda'
         for x in (prefetch_to_device(batches, to_device, dev) if overlapped else batches):
+            cal.begin_batch()
             if graphs:
                 if static_in is None:
                     static_in = torch.empty(x.shape, dtype=torch.float32, device=dev)

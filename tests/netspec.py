@@ -51,6 +51,13 @@ def make_data(name, seed, steps, batch):
 
 
 # ------------------------------------------------------------------------------------------------ torch.nn.Module (our executor)
+class RefGemm(torch.nn.Linear):
+    """The reference's Gemm forward, operation for operation (executor/op/torch/default.py:2055-2063): a matmul, then the bias add."""
+
+    def forward(self, x):
+        return 1.0 * torch.matmul(x, self.weight.transpose(0, 1)) + 1.0 * self.bias
+
+
 class SpecNet(torch.nn.Module):
     """Executes the spec with one sub-module per operation (names = the spec's names), so that module hooks see every op."""
 
@@ -62,7 +69,7 @@ class SpecNet(torch.nn.Module):
             if o['op'] == 'Conv':
                 m = torch.nn.Conv2d(o['cin'] * o['group'], o['cout'], o['k'], stride=o['stride'], padding=o['pad'], groups=o['group'])
             elif o['op'] == 'Gemm':
-                m = torch.nn.Linear(o['cin'], o['cout'])
+                m = RefGemm(o['cin'], o['cout'])
             elif o['op'] == 'Relu':
                 m = torch.nn.ReLU()
             elif o['op'] == 'MaxPool':

@@ -84,3 +84,73 @@ def test_pack_unpack_minmax_and_shards():
     for n, w in ((4096, 8), (13, 4), (8, 8), (3, 8)):
         got = sorted(i for r in range(w) for i in shard_indices(n, r, w))
         assert got == list(range(n))
+
+
+def _reduce_worker(rank, world, port, out_dir, starve_rank):
+    """RuntimeCalibrationPass._reduce on observers with hand-made statistics (the collectors themselves need a GPU; the exchange does not)."""
+    import types
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from ppq_b200 import LinearQuantizationConfig
+    from ppq_b200.calibration import RuntimeCalibrationPass
+    from ppq_b200.observer import TorchHistObserver, TorchMinMaxObserver, TorchPercentileObserver
+    g = torch.Generator().manual_seed(7 + rank)
+
+    def slot(channels=None, bins=0):
+        lo, hi = -torch.rand(1, generator=g) * (rank + 1), torch.rand(1, generator=g) * (3 - rank)
+        s = types.SimpleNamespace(minmax=torch.cat([lo, hi]), cmins=None, cmaxs=None, hist=None)
+        if channels: s.cmins, s.cmaxs = -torch.rand(channels, generator=g) * (rank + 1), torch.rand(channels, generator=g) * (2 - rank)
+        if bins: s.hist = torch.randint(0, 50, (bins,), generator=g, dtype=torch.int32)
+        return s
+
+    def make(cls, cfg, s, observed=3):
+        ob = object.__new__(cls)
+        ob._quant_cfg, ob._slot, ob._observed = cfg, s, (0 if rank == starve_rank else observed)
+        return ob
+    t_obs = make(TorchMinMaxObserver, LinearQuantizationConfig(), slot())
+    c_obs = make(TorchMinMaxObserver, LinearQuantizationConfig(channel_axis=1), slot(channels=6))
+    h_obs = make(TorchHistObserver, LinearQuantizationConfig(calibration='kl'), slot(bins=32))
+    p_obs = object.__new__(TorchPercentileObserver)
+    p_obs._quant_cfg = LinearQuantizationConfig(calibration='percentile')
+    p_obs._percentile_collector = [] if rank == starve_rank else [torch.tensor([[10.0 * rank + j, -(10.0 * rank + j)]]) for j in range(2)]
+    table = {1: t_obs, 2: c_obs, 3: h_obs, 4: p_obs}
+    pas = RuntimeCalibrationPass(method=None)
+    pas._observers = {'op': types.SimpleNamespace(hook=types.SimpleNamespace(_observer_table=table))}
+    before = {'t': t_obs._slot.minmax.clone(), 'cmin': c_obs._slot.cmins.clone(), 'cmax': c_obs._slot.cmaxs.clone(),
+              'h_mm': h_obs._slot.minmax.clone(), 'hist': h_obs._slot.hist.clone()}
+    err = None
+    try:
+        pas._reduce(1)
+        pas._reduce(2)
+    except RuntimeError as e:
+        err = str(e)
+    torch.save({'before': before, 'err': err, 't': t_obs._slot.minmax, 'cmin': c_obs._slot.cmins, 'cmax': c_obs._slot.cmaxs,
+                'h_mm': h_obs._slot.minmax, 'hist': h_obs._slot.hist,
+                'pct': torch.cat(p_obs._percentile_collector) if p_obs._percentile_collector else None}, os.path.join(out_dir, f'q{rank}.pt'))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_reduce_covers_per_channel_statistics_and_percentile_pairs(tmp_path):
+    """per-channel min / max vectors must be exchanged too, in the same packed MAX all-reduce."""
+    world, port = 2, _free_port()
+    mp.spawn(_reduce_worker, args=(world, port, str(tmp_path), -1), nprocs=world, join=True)
+    r = [torch.load(tmp_path / f'q{k}.pt') for k in range(world)]
+    assert r[0]['err'] is None and r[1]['err'] is None
+    for key, fn in (('cmin', torch.minimum), ('cmax', torch.maximum)):
+        want = fn(r[0]['before'][key], r[1]['before'][key])
+        assert torch.equal(r[0][key], want) and torch.equal(r[1][key], want)
+    for key in ('t', 'h_mm'):
+        want = torch.stack([torch.minimum(r[0]['before'][key][0], r[1]['before'][key][0]), torch.maximum(r[0]['before'][key][1], r[1]['before'][key][1])])
+        assert torch.equal(r[0][key], want) and torch.equal(r[1][key], want)
+    assert torch.equal(r[0]['hist'], r[0]['before']['hist'] + r[1]['before']['hist']) and torch.equal(r[1]['hist'], r[0]['hist'])
+    # percentile pairs come back in global sample order: rank 0 batch 0, rank 1 batch 0, rank 0 batch 1, rank 1 batch 1
+    assert r[0]['pct'][:, 0].tolist() == [0.0, 10.0, 1.0, 11.0] and torch.equal(r[0]['pct'], r[1]['pct'])
+
+
+def test_reduce_fails_on_every_rank_when_one_rank_saw_no_batch(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_reduce_worker, args=(world, port, str(tmp_path), 1), nprocs=world, join=True)
+    r = [torch.load(tmp_path / f'q{k}.pt') for k in range(world)]
+    assert all(x['err'] is not None and 'observed no calibration batch' in x['err'] for x in r)

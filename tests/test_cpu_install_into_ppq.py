@@ -1,26 +1,19 @@
 """Drop-in check against the REAL reference package (only where /root/reference exists, i.e. the build container): after
 ppq_b200.install.install(), ppq.core.ffi.CUDA.* reaches ppq_b200/_C.so with the reference's own argument orders, and
 ENABLE_CUDA_KERNEL() no longer tries to JIT-compile anything.  No GPU here, so the calls must fail with OUR loud CPU-tensor error."""
-import os
-import sys
-
 import pytest
 import torch
 
-REF = os.environ.get('PPQ_REFERENCE_ROOT', '/root/reference')
+import ppq_b200
+
+import refppq
 
 
 @pytest.fixture(scope='module')
 def ppq():
-    if not os.path.isdir(os.path.join(REF, 'ppq')):
-        pytest.skip('reference package not present on this machine')
-    os.environ['PROTOCOL_BUFFERS_PYTHON_IMPLEMENTATION'] = 'python'
-    from unittest.mock import MagicMock
-    for m in ['onnx', 'onnx.helper', 'onnx.numpy_helper', 'onnx.mapping', 'onnx.checker', 'onnx.shape_inference']:
-        sys.modules.setdefault(m, MagicMock())
-    sys.path.insert(0, REF)
-    import ppq as _ppq
-    return _ppq
+    mod = refppq.load()
+    if mod is None: pytest.skip('reference package not present on this machine (neither /root/reference nor baseline/_ref)')
+    return mod
 
 
 def test_install_routes_every_ffi_call_to_our_extension(ppq):
@@ -66,12 +59,24 @@ def test_install_routes_every_ffi_call_to_our_extension(ppq):
 
 def test_observer_table_replaced(ppq):
     import ppq.quantization.observer as ref_obs
+    import ppq.quantization.optim.calibration as ref_cal
+    import ppq.quantization.optim.ssd as ref_ssd
     import ppq_b200.install
     import ppq_b200.observer as ours
     before = dict(ref_obs.OBSERVER_TABLE)
+    ref_hist, ref_mse = ref_cal.TorchHistObserver, ref_cal.TorchMSEObserver
     ppq_b200.install.install(replace_observers=True)
     try:
-        assert ref_obs.OBSERVER_TABLE['minmax'] is ours.TorchMinMaxObserver and ref_obs.OBSERVER_TABLE['kl'] is ours.TorchHistObserver
+        for k in ('minmax', 'kl', 'mse', 'percentile'):
+            assert ref_obs.OBSERVER_TABLE[k] is ours.OBSERVER_TABLE[k]
+        # the reference keeps an observer for calibration phase 2 only if `type(observer) in {TorchHistObserver, TorchMSEObserver}` as
+        # imported by optim/calibration.py:10-13 (:195) and optim/ssd.py:14 (:445): the replaced classes must satisfy that test
+        cfg = ppq_b200.LinearQuantizationConfig(calibration='kl')
+        assert type(ref_obs.OBSERVER_TABLE['kl'](watch_on=None, quant_cfg=cfg)) in {ref_cal.TorchHistObserver, ref_cal.TorchMSEObserver}
+        assert type(ref_obs.OBSERVER_TABLE['mse'](watch_on=None, quant_cfg=cfg)) in {ref_cal.TorchHistObserver, ref_cal.TorchMSEObserver}
+        assert type(ref_obs.OBSERVER_TABLE['kl'](watch_on=None, quant_cfg=cfg)) in {ref_ssd.TorchHistObserver}
+        assert type(ref_obs.OBSERVER_TABLE['minmax'](watch_on=None, quant_cfg=cfg)) not in {ref_cal.TorchHistObserver, ref_cal.TorchMSEObserver}
     finally:
         ppq_b200.install.uninstall()                      # leave the imported reference as found (other tests use its CPU path)
     assert ref_obs.OBSERVER_TABLE == before
+    assert ref_cal.TorchHistObserver is ref_hist and ref_cal.TorchMSEObserver is ref_mse and ref_ssd.TorchHistObserver is ref_hist

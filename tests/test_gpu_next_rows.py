@@ -47,12 +47,15 @@ def close(a, b, rtol=1e-4, atol=1e-6):
 def test_quantile_vs_sort_oracle_and_reference(ext, ref, oracle):
     g = torch.Generator(device='cuda').manual_seed(0)
     for n in (1, 2, 3, 17, 1000, 4099, 401408, (1 << 21) + 5):
-        for kind in ('randn', 'relu', 'negrelu', 'const', 'ints'):
+        for kind in ('randn', 'relu', 'negrelu', 'const', 'ints', 'close'):
             x = torch.randn(n, device='cuda', generator=g) * 3
             if kind == 'relu': x = torch.relu(x)
             if kind == 'negrelu': x = -torch.relu(x)                              # half of the elements are -0.0: the bucket of +0 must take them
             if kind == 'const': x = torch.full((n,), -1.25, device='cuda')
             if kind == 'ints': x = torch.randint(-5, 5, (n,), device='cuda', generator=g).float()
+            if kind == 'close':                                                   # three values that share the top 11 / top 22 key bits: a bucket too
+                vals = torch.tensor([1.0, 1.0 + 2.0 ** -23, 1.0 + 2.0 ** -12], device='cuda')   # big to compact (n = 2 M) must be refined by passes 1 and 2
+                x = vals[torch.randint(0, 3, (n,), device='cuda', generator=g)]
             if n > 8: x[3] = -0.0; x[5] = 0.0
             for q in (0.9999, 0.999, 0.5, 1.0, 0.0):
                 got = ext.Quantile_T(x, q)
@@ -71,6 +74,32 @@ def test_quantile_vs_sort_oracle_and_reference(ext, ref, oracle):
     v = base[1:]
     assert torch.equal(ext.Quantile_T(v, 0.99), torch.stack([torch.sort(v)[0][int(np.rint(np.float32(v.numel()) * np.float32(0.99)))],
                                                              torch.sort(v)[0][int(np.rint(np.float32(v.numel()) * (np.float32(1) - np.float32(0.99))))]]))
+
+
+def test_multi_tensor_quantile_matches_single_launches(ext):
+    """Multi_Quantile_T: one launch per pass over a table of tensors (ragged sizes, tiny tensors, post-ReLU tensors) must select the very same
+    elements as one Quantile_T per tensor -- with a workspace big enough to compact the selected buckets, and with a tiny one that forces the
+    refine-by-histogram fallback on every level."""
+    g = torch.Generator(device='cuda').manual_seed(5)
+    sizes = [1, 3, 1000, 4099, 401408, 150528, 7, (1 << 20) + 3, 25088, 2]
+    xs = []
+    for i, n in enumerate(sizes):
+        x = torch.randn(n, device='cuda', generator=g) * (i + 1)
+        if i % 3 == 1: x = torch.relu(x)
+        if i == 5: x = torch.randint(-3, 3, (n,), device='cuda', generator=g).float()
+        xs.append(x)
+    slots = list(range(len(xs)))[::-1]                                           # results land in the slot the descriptor names
+    descs = torch.tensor([[x.data_ptr(), x.numel(), s] for x, s in zip(xs, slots)], dtype=torch.int64, device='cuda')
+    for q in (0.9999, 0.99, 0.5):
+        want = torch.stack([ext.Quantile_T(x, q) for x in xs])
+        for cap in (1 << 16, 64):
+            ws = torch.empty(ext.Multi_Quantile_Workspace_Bytes(len(xs), cap), dtype=torch.uint8, device='cuda')
+            out = torch.full((len(xs), 3), -7.0, device='cuda')                  # out_stride 3: the third column must stay untouched
+            ext.Multi_Quantile_T(descs, max(sizes), q, out, 3, ws, cap)
+            assert torch.equal(out[slots, :2], want), (q, cap, out, want)
+            assert bool((out[:, 2] == -7.0).all())
+    with pytest.raises(RuntimeError, match='workspace is too small'):
+        ext.Multi_Quantile_T(descs, max(sizes), 0.5, torch.zeros(len(xs), 2, device='cuda'), 2, torch.empty(16, dtype=torch.uint8, device='cuda'), 64)
 
 
 def test_isotone_top2_bottom2(ext, ref):

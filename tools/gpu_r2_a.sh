@@ -1,0 +1,8 @@
+#!/bin/bash
+# round 2, GPU call A: the whole GPU suite (new: graph-level parity with the real reference package, 2-pass select, arena percentile / mse),
+# smoke, quantile micro-benchmarks.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=30 2>&1 | grep -v "^  \|^$\|Warning\|warn" | cut -c1-400 | tail -80 > gpurun_out/r2a_tests.log; tail -60 gpurun_out/r2a_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 300 python tools/kbench.py --only quantile,kl --reps 20 > gpurun_out/r2a_kbench.txt 2>&1; cat gpurun_out/r2a_kbench.txt

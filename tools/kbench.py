@@ -84,7 +84,16 @@ def main():
         report('linear_quant_t ROUND_HALF_FAR_FROM_ZERO (run-time mode)', timeit(lambda i: ext.QuantizeTensor_LT(xs[i], one, zero, -128, 127, 4), args.reps, nbuf), 8)
         report('linear_quant_t toInt8', timeit(lambda i: ext.QuantizeTensor_toInt(xs[i], one, zero, -128, 127, -1000, 0, 8), args.reps, nbuf), 5)
     if 'quantile' in only:
-        report('quantile_t q=0.9999 (3-pass radix select, 12 B/elem)', timeit(lambda i: ext.Quantile_T(xs[i], 0.9999), args.reps, nbuf), 12)
+        # algorithmic traffic of the percentile observer is 4 B/element; the select streams the tensor twice
+        report('quantile_t q=0.9999 randn (2 passes + finish)', timeit(lambda i: ext.Quantile_T(xs[i], 0.9999), args.reps, nbuf), 4)
+        report('quantile_t q=0.9999 relu (zero bucket refined)', timeit(lambda i: ext.Quantile_T(xr[i % 3], 0.9999), args.reps, 3), 4)
+        sizes = [n // 16] * 16
+        parts = [[x[k * (n // 16):(k + 1) * (n // 16)] for k in range(16)] for x in xs]
+        descs = [torch.tensor([[t.data_ptr(), t.numel(), k] for k, t in enumerate(p)], dtype=torch.int64, device=dev) for p in parts]
+        cap = 1 << 16
+        ws = torch.empty(ext.Multi_Quantile_Workspace_Bytes(16, cap), dtype=torch.uint8, device=dev)
+        out = torch.zeros(16, 2, device=dev)
+        report('multi_quantile_t 16 tensors of n/16 (one table)', timeit(lambda i: ext.Multi_Quantile_T(descs[i], n // 16, 0.9999, out, 2, ws, cap), args.reps, nbuf), 4)
     if 'lc' in only:
         for shape, axis in (((n // 4608, 4608), 0), ((n // 512, 512), 0), ((n // 64, 64), 0), ((8, n // 8 // 3136, 3136), 1), ((n // 9, 9), 0), ((n // 768, 768), 1)):
             C = shape[axis]
