@@ -205,18 +205,31 @@ class CpuPipeline:
                   for lo, hi in zip(flat.min(dim=1)[0].tolist(), flat.max(dim=1)[0].tolist())]
             op.w._scale, op.w._offset, op.w.state = torch.tensor(sc, dtype=torch.float32), torch.zeros(len(sc)), 'ACTIVATED'
 
+    def observed_all(self):
+        """The activation configs that take part in calibration whatever their current state (group roots): what observed() returned before."""
+        out = []
+        for op in self.ops:
+            out += [(c.label, c) for c in op.ins if c.root is c]
+            if op.out.root is op.out: out.append((op.out.label, op.out))
+        return out
+
     @torch.no_grad()
-    def calibrate(self, batches, method='kl'):
+    def calibrate(self, batches, method='kl', return_search_seconds=False):
         self.observers = {id(c): _Observer(method) for _, c in self.observed()}
         cfgs = {id(c): c for _, c in self.observed()}
         self.phase = 1
         for x in batches: self.forward(x)
+        t0 = time.perf_counter()
         for k, ob in self.observers.items(): ob.render(cfgs[k], 1)
+        search = time.perf_counter() - t0
         if method in ('kl', 'mse'):
             self.phase = 2
             for x in batches: self.forward(x)
+            t0 = time.perf_counter()
             for k, ob in self.observers.items(): ob.render(cfgs[k], 2)
+            search += time.perf_counter() - t0
         self.observers, self.phase = {}, 0
+        if return_search_seconds: return search                              # the render / scale-search part (once per calibration, not per batch)
         return {c.label: c for c in cfgs.values()}
 
     @torch.no_grad()

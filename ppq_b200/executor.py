@@ -129,7 +129,7 @@ class TorchExecutor:
         self._calls: Dict[int, int] = {}
         self._names = {id(m): n for n, m in self.model.named_modules()}
         self._hooks, self._collect, self._collected, self._sink = None, False, None, None
-        self._tracing, self._wq, self._swapped = True, {}, {}
+        self._tracing, self._wq, self._swapped, self._bypass = True, {}, {}, False
         self._produced = {}                                            # id(tensor) -> (operation, tensor, version at production)
         self._quant_fn = PPQuantFunction
         for m in self.model.modules():
@@ -248,6 +248,7 @@ class TorchExecutor:
             src.consumers.append((op, i))
 
     def _pre(self, module, args):
+        if self._bypass: return None                                      # plain fp32 forward of the network (bench breakdown)
         tensors = [a for a in args if isinstance(a, torch.Tensor)]
         op = self._op_of(module, len(tensors))
         if self._tracing:
@@ -274,6 +275,7 @@ class TorchExecutor:
         return None
 
     def _post(self, module, args, output):
+        if self._bypass: return None
         op = self._op_of(module)
         self._calls[id(module)] = self._calls.get(id(module), 0) + 1
         if self._tracing:
@@ -525,37 +527,52 @@ def graphwise_error_analyse(executor: TorchExecutor, batches, to_device=None) ->
     return {n: v[0] / max(v[1], 1) for n, v in acc.items()}
 
 
-def e2e_calibration_benchmark(batch: int, steps: int, warmup: int, device, world: int = 1, seed: int = 0, graphs: bool = False):
-    """bench.py's `e2e`: ResNet-50 (random init, BN folded) calibrated end to end through the public API -- images in pinned host
-    memory, H2D copy of every batch inside the timed region (both phases), torch forward with per-forward weight fake-quant,
-    multi-tensor collectors, the two all-reduces, on-device KL search and a D2H read of the resulting scales."""
+def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int, device, world: int = 1, seed: int = 0, graphs: bool = False):
+    """bench.py's `e2e`: ResNet-50 (random init, BN folded) calibrated end to end through the public API -- `batches` x `batch` images in pinned
+    host memory (this rank's share of the calibration set), H2D copy of every batch inside the timed region (both phases), torch forward with
+    per-forward weight fake-quant, multi-tensor collectors, the two all-reduces, on-device KL search and a D2H read of the resulting scales.
+    One step = one whole calibration; `steps` of them are timed after warm-up calibrations at the timed shape have converged (two consecutive
+    ones within 5 %: cuDNN autotuning, allocator growth, descriptor caches and clocks all settle there, not in a 2-batch dry run)."""
     import torch.distributed as dist
     import torchvision
-    torch.manual_seed(seed)
+    torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
     model = torchvision.models.resnet50(weights=None).eval()
     ex = TorchExecutor(model.to(device), torch.zeros(2, 3, 224, 224, device=device))
     ex.quantize_parameters()
-    g = torch.Generator().manual_seed(seed + 1)
-    host = [torch.rand(batch, 3, 224, 224, generator=g).pin_memory() for _ in range(steps)]
+    g = torch.Generator().manual_seed(1000 + seed)                         # every rank calibrates its OWN shard of the sample set
+    host = [torch.rand(batch, 3, 224, 224, generator=g).pin_memory() for _ in range(batches)]
     stream = torch.cuda.current_stream()
-
     act_cfgs = ex.observed_configs()
+    to_dev = lambda x: x.to(device, non_blocking=True)                     # noqa: E731
 
     def reset():
         for c in act_cfgs: c.state = QuantizationStates.INITIAL
 
-    def run(batches):
-        cal = calibrate_arena(ex, batches, method='kl', to_device=lambda x: x.to(device, non_blocking=True), graphs=graphs)
-        return cal.scale.cpu()                                            # D2H of the result (synchronises)
+    def run():
+        cal = calibrate_arena(ex, host, method='kl', to_device=to_dev, graphs=graphs)
+        s = cal.scale.cpu()                                               # D2H of the result (synchronises)
+        reset()
+        return s
 
-    for _ in range(max(warmup, 1)):
-        run(host[:2]); reset()
+    def timed(fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); a.record(stream); out = fn(); b.record(stream); torch.cuda.synchronize()
+        return a.elapsed_time(b), out
+
+    warm = []
+    while len(warm) < max(warmup, 2) or (len(warm) < 8 and abs(warm[-1] - warm[-2]) > 0.05 * warm[-1]):
+        warm.append(timed(run)[0])
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_step = []
     t0.record(stream)
-    scales = run(host)
+    for _ in range(steps):
+        a = torch.cuda.Event(enable_timing=True); a.record(stream)
+        scales = run()
+        b = torch.cuda.Event(enable_timing=True); b.record(stream)
+        per_step.append((a, b))
     t1.record(stream)
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
@@ -563,8 +580,32 @@ def e2e_calibration_benchmark(batch: int, steps: int, warmup: int, device, world
     if world > 1:
         t = torch.tensor([ms], device=device); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
     assert bool(torch.isfinite(scales).all()) and bool((scales > 0).all())
-    return {'value': round(world * steps * batch / (ms * 1e-3), 1), 'unit': 'imgs/s',
-            'h2d_bytes_per_step': 2 * batch * 3 * 224 * 224 * 4, 'd2h_bytes_per_step': int(scales.numel() * 4 / steps) + 1,
-            'ms_per_step': round(ms / steps, 3), 'steps': steps, 'observed_tensors': int(scales.numel()), 'cuda_graphs': graphs,
+
+    # ---- breakdown (untimed, after the measurement): where a calibration batch's time goes
+    def forwards(bypass):
+        for _ in range(2):                                                # two passes over the set, like the two phases
+            for x in prefetch_to_device(host, to_dev, device):
+                if bypass:
+                    ex._bypass = True
+                    try: ex.model(x)
+                    finally: ex._bypass = False
+                else:
+                    ex.forward(x, sink=lambda k, t: True)                 # hooks + per-forward weight fake-quant, no collector launch
+    with torch.no_grad():
+        pure = min(timed(lambda: forwards(True))[0] for _ in range(2))
+        hooked = min(timed(lambda: forwards(False))[0] for _ in range(2))
+        h2d = min(timed(lambda: [to_dev(x) for x in host for _ in range(2)])[0] for _ in range(2))
+    nb2 = 2.0 * batches
+    step_ms = [a.elapsed_time(b) for a, b in per_step]
+    total = ms / steps
+    return {'value': round(world * steps * batches * batch / (ms * 1e-3), 1), 'unit': 'imgs/s',
+            'h2d_bytes_per_step': 2 * batches * batch * 3 * 224 * 224 * 4, 'd2h_bytes_per_step': int(scales.numel() * 4),
+            'ms_per_step': round(total, 3), 'steps': steps, 'step': f'one whole calibration: {batches} batches x {batch} images, both phases',
+            'step_ms': {'min': round(min(step_ms), 3), 'median': round(sorted(step_ms)[len(step_ms) // 2], 3), 'max': round(max(step_ms), 3)},
+            'warmup_calibrations_ms': [round(w, 2) for w in warm],
+            'observed_tensors': int(scales.numel()), 'cuda_graphs': graphs,
+            'breakdown_ms_per_batch_pass': {'forward_fp32_cudnn': round(pure / nb2, 3), 'hooks_and_weight_fakequant': round((hooked - pure) / nb2, 3),
+                                            'collectors_exchange_search': round((total - hooked) / nb2, 3),
+                                            'h2d_copy_overlapped': round(h2d / nb2, 3), 'total': round(total / nb2, 3)},
             'what': 'pinned-host images -> H2D -> torch ResNet-50 forward (fp32, cuDNN) with per-forward INT8 per-channel weight fake-quant '
                     '-> multi-tensor min/max (phase 1) / histogram (phase 2) -> all-reduce -> on-device KL search -> scales D2H'}
