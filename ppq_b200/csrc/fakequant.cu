@@ -173,6 +173,72 @@ ew_channel_vec_kernel(const float *__restrict__ x, OutT *__restrict__ y, uint32_
     channel_vec_body<Op, OutT>(x, y, n4, C, div_epc4, div_C, scale, offset, plan, blockIdx.x * kThreads + threadIdx.x, gridDim.x * kThreads);
 }
 
+// ---- per-channel, short rows (4 <= epc < 512): per-row operators from a shared-memory table -------------------------------------------
+// A CTA walks contiguous tiles of 1024 vectors (16 KB; tiles round-robin over the grid, inside a tile every warp owns a contiguous 2 KB
+// segment, 4 x 128-bit loads in flight per lane).  The rows a tile touches are known from two divisions per TILE; their operators -- exact
+// reciprocal with its range check, integer offset -- are built ONCE per row by the first threads of the CTA into a 16-byte-per-row table
+// while the tile's loads are in flight, so an element pays one table read per vector (VEC4: rows are a multiple of 4 elements, a vector
+// never straddles a row) or per element (any epc >= 4: the walker steps to the next entry at a row end) instead of two multiply-high
+// divisions, two global loads, a reciprocal and a float->int conversion per vector.
+constexpr int kTileVec = kThreads * kUnroll;                            // 1024 vectors = 4096 elements
+constexpr int kTabRows = 4 * kTileVec / 4 + 2;                          // rows a tile can touch when epc >= 4
+template <class Op, class OutT, bool VEC4>
+__global__ void __launch_bounds__(kThreads)
+ew_channel_table_kernel(const float *__restrict__ x, OutT *__restrict__ y, uint32_t n, uint32_t epc, int C, FastDiv32 div_epc, FastDiv32 div_C,
+                        const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
+    __shared__ float4 tab[kTabRows];
+    const typename Op::Plan plan(p);
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    const uint32_t groups = (n + 3u) >> 2;                              // VEC4: n % 4 == 0
+    const uint32_t n4 = n >> 2;                                         // whole vectors
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = blockIdx.x * (uint32_t)kTileVec; base < groups; base += gridDim.x * (uint32_t)kTileVec) {
+        const uint32_t v0 = base + warp * (32 * kUnroll) + lane;
+        float4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) if (v0 + j * 32 < n4) v[j] = ld_stream4(x4 + v0 + j * 32);
+        const uint32_t e_first = base << 2;
+        const uint32_t e_last = min(n, (base + (uint32_t)kTileVec) << 2) - 1u;
+        const uint32_t r0 = div_epc.quot(e_first), rows = div_epc.quot(e_last) - r0 + 1u;
+        for (uint32_t i = threadIdx.x; i < rows; i += kThreads) {
+            const uint32_t row = r0 + i, c = row - div_C.quot(row) * (uint32_t)C;
+            tab[i] = Op::entry(__ldg(scale + c), __ldg(offset + c));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+            const uint32_t vi = v0 + j * 32;
+            if (vi >= groups) continue;
+            const uint32_t e0 = vi << 2;
+            const uint32_t row = div_epc.quot(e0);
+            if constexpr (VEC4) {
+                const Op op(plan, tab[row - r0]);
+                Emit<Op, OutT>::vec(op, v[j], y, (int64_t)vi);
+            } else {
+                uint32_t col = e0 - row * epc, idx = row - r0;
+                if (vi < n4) {
+                    const float in[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                    OutT out[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const Op op(plan, tab[idx]);
+                        out[k] = Emit<Op, OutT>::one(op, in[k]);
+                        if (++col == epc) { col = 0; ++idx; }
+                    }
+                    Emit<Op, OutT>::store4(y, vi, out[0], out[1], out[2], out[3]);
+                } else {                                                // the <= 3 elements after the last whole vector
+                    for (uint32_t e = e0; e < n; e++) {
+                        const Op op(plan, tab[idx]);
+                        y[e] = Emit<Op, OutT>::one(op, ld_stream1(x + e));
+                        if (++col == epc) { col = 0; ++idx; }
+                    }
+                }
+            }
+        }
+        __syncthreads();                                                // the next tile rebuilds the table
+    }
+}
+
 // ---- per-channel, channel-last (epc == 1, C % 4 == 0): x is [rows, C], element (r, c) belongs to channel c ---------------------
 // The grid-stride is rounded down to a multiple of C/4, so every thread keeps meeting the same four channels: their operators
 // (exact reciprocals, integer offsets) are built once per thread and the loop body costs what the per-tensor kernel costs.
@@ -384,12 +450,23 @@ static int launch_channel(const float *x, OutT *y, int64_t n, int64_t epc, int C
                           typename Op::Params p, cudaStream_t st) {
     if (n <= 0 || epc <= 0 || C <= 0 || !x || !y || !scale || !offset) return (int)cudaErrorInvalidValue;
     if (epc > 0x7fffffffLL || n % epc != 0) return (int)cudaErrorInvalidValue;
-    if (epc % 4 == 0 && aligned16(x) && out_aligned<OutT>(y)) {
+    const bool al = aligned16(x) && out_aligned<OutT>(y);
+    const auto table_grid = [&]() {
+        int64_t tiles = ((n + 3) / 4 + kTileVec - 1) / kTileVec;
+        const int64_t cap = (int64_t)sm_count() * 6;                    // 40+ registers, 16.6 KB of table: six CTAs per SM
+        return (int)(tiles < cap ? tiles : cap);
+    };
+    if (epc % 4 == 0 && al) {
         const int64_t n4 = n / 4;
         if (n4 <= 0x1fffffffLL && epc / 4 >= 128) {
             const int grid = grid_for(n4, kThreads, kUnroll, 16);
             ew_channel_seg_kernel<Op, OutT><<<grid, kThreads, 0, st>>>(x, y, (uint32_t)n4, C, (uint32_t)(epc / 4), FastDiv32((uint32_t)(epc / 4)),
                                                                           FastDiv32((uint32_t)C), scale, offset, p);
+            return (int)cudaGetLastError();
+        }
+        if (n <= 0x7fffffffLL && variant_of(kVarChannel) == 0) {        // short rows: per-row operators from a shared-memory table
+            ew_channel_table_kernel<Op, OutT, true><<<table_grid(), kThreads, 0, st>>>(x, y, (uint32_t)n, (uint32_t)epc, C, FastDiv32((uint32_t)epc),
+                                                                                       FastDiv32((uint32_t)C), scale, offset, p);
             return (int)cudaGetLastError();
         }
         if (n4 <= 0x7fffffffLL) {
@@ -399,7 +476,7 @@ static int launch_channel(const float *x, OutT *y, int64_t n, int64_t epc, int C
             return (int)cudaGetLastError();
         }
     }
-    if (epc == 1 && C % 4 == 0 && aligned16(x) && out_aligned<OutT>(y)) {
+    if (epc == 1 && C % 4 == 0 && al) {
         const int64_t n4 = n / 4, C4 = C / 4;
         const int grid = grid_for(n4, kThreads, kUnroll, 8);
         const int64_t threads = (int64_t)grid * kThreads;
@@ -407,6 +484,11 @@ static int launch_channel(const float *x, OutT *y, int64_t n, int64_t epc, int C
             ew_channel_last_kernel<Op, OutT><<<grid, kThreads, 0, st>>>(x, y, n4, (uint32_t)C4, (uint32_t)(threads / C4 * C4), scale, offset, p);
             return (int)cudaGetLastError();
         }
+    }
+    if (epc >= 4 && al && n <= 0x7fffffffLL && variant_of(kVarChannel) == 0) {      // ragged short rows (depth-wise 3x3: epc 9)
+        ew_channel_table_kernel<Op, OutT, false><<<table_grid(), kThreads, 0, st>>>(x, y, (uint32_t)n, (uint32_t)epc, C, FastDiv32((uint32_t)epc),
+                                                                                    FastDiv32((uint32_t)C), scale, offset, p);
+        return (int)cudaGetLastError();
     }
     const int grid = grid_for((n + 3) / 4, kThreads, 1, 8);
     ew_channel_generic_kernel<Op, OutT><<<grid, kThreads, 0, st>>>(x, y, n, epc, C, FastDiv((uint32_t)epc), FastDiv((uint32_t)C),
@@ -445,6 +527,21 @@ int launch_linear_quant_t_tma(const float *x, float *y, int64_t n, const float *
 
 extern "C" {
 
+// Every rounding policy is a compile-time instantiation behind one switch (the run-time-mode operator, LinearOp<-1>, costs 20 points of
+// HBM peak: its uniform branches and the fp32 "+ .5" forms of all four half-way modes stay live in the loop).
+#define PPQB_DISPATCH_MODE(rounding, CALL)                          \
+    switch (rounding) {                                             \
+    case RND_HALF_EVEN:          { constexpr int M_ = RND_HALF_EVEN; CALL; }          \
+    case RND_HALF_UP:            { constexpr int M_ = RND_HALF_UP; CALL; }            \
+    case RND_HALF_DOWN:          { constexpr int M_ = RND_HALF_DOWN; CALL; }          \
+    case RND_HALF_TOWARDS_ZERO:  { constexpr int M_ = RND_HALF_TOWARDS_ZERO; CALL; }  \
+    case RND_HALF_FAR_FROM_ZERO: { constexpr int M_ = RND_HALF_FAR_FROM_ZERO; CALL; } \
+    case RND_TO_NEAR_INT:        { constexpr int M_ = RND_TO_NEAR_INT; CALL; }        \
+    case RND_UP:                 { constexpr int M_ = RND_UP; CALL; }                 \
+    case RND_DOWN:               { constexpr int M_ = RND_DOWN; CALL; }               \
+    default: break;                                                 \
+    }
+
 int ppq_b200_linear_quant_t(const float *x, float *y, int64_t n, const float *scale, const float *offset,
                             int qmin, int qmax, int rounding, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -461,21 +558,16 @@ int ppq_b200_linear_quant_t(const float *x, float *y, int64_t n, const float *sc
             else ew_tensor_kernel<Op, float, true, 4, 256><<<grid_for(n4, 256, 4, 8), 256, 0, st>>>(x, y, n, scale, offset, p);                 // 4 loads, persistent
             return (int)cudaGetLastError();
         }
-        return launch_tensor<LinearOp<0>, float>(x, y, n, scale, offset, {qmin, qmax, 0}, st);
     }
-    if (rounding == RND_HALF_UP)              // the one other policy a shipped quantizer selects (NXPQuantizer.py:122): compile-time mode as well
-        return launch_tensor<LinearOp<RND_HALF_UP>, float>(x, y, n, scale, offset, {qmin, qmax, RND_HALF_UP}, st);
-    return launch_tensor<LinearOp<-1>, float>(x, y, n, scale, offset, {qmin, qmax, rounding}, st);
+    PPQB_DISPATCH_MODE(rounding, return (launch_tensor<LinearOp<M_>, float>(x, y, n, scale, offset, {qmin, qmax, M_}, st)))
+    return launch_tensor<LinearOp<-1>, float>(x, y, n, scale, offset, {qmin, qmax, rounding}, st);     // unknown ids: the reference's `default` branch
 }
 
 int ppq_b200_linear_quant_c(const float *x, float *y, int64_t n, int64_t epc, int C, const float *scale, const float *offset,
                             int qmin, int qmax, int rounding, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (qmin > qmax) return (int)cudaErrorInvalidValue;
-    if (rounding == RND_HALF_EVEN)
-        return launch_channel<LinearOp<0>, float>(x, y, n, epc, C, scale, offset, {qmin, qmax, 0}, st);
-    if (rounding == RND_HALF_UP)
-        return launch_channel<LinearOp<RND_HALF_UP>, float>(x, y, n, epc, C, scale, offset, {qmin, qmax, RND_HALF_UP}, st);
+    PPQB_DISPATCH_MODE(rounding, return (launch_channel<LinearOp<M_>, float>(x, y, n, epc, C, scale, offset, {qmin, qmax, M_}, st)))
     return launch_channel<LinearOp<-1>, float>(x, y, n, epc, C, scale, offset, {qmin, qmax, rounding}, st);
 }
 
@@ -486,6 +578,10 @@ int ppq_b200_linear_quant_t_toint(const float *x, void *q, int out_bits, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     if (qmin > qmax) return (int)cudaErrorInvalidValue;
     if (!toint_bits_ok(out_bits)) return (int)cudaErrorInvalidValue;
+    if (rounding == RND_HALF_EVEN) {                                   // the policy every shipped quantizer but one selects: compile-time
+        if (out_bits == 8) return launch_tensor<LinearOp<0>, int8_t>(x, (int8_t *)q, n, scale, offset, {qmin, qmax, 0}, st);
+        return launch_tensor<LinearOp<0>, int32_t>(x, (int32_t *)q, n, scale, offset, {qmin, qmax, 0}, st);
+    }
     if (out_bits == 8) return launch_tensor<LinearOp<-1>, int8_t>(x, (int8_t *)q, n, scale, offset, {qmin, qmax, rounding}, st);
     return launch_tensor<LinearOp<-1>, int32_t>(x, (int32_t *)q, n, scale, offset, {qmin, qmax, rounding}, st);
 }
@@ -495,6 +591,10 @@ int ppq_b200_linear_quant_c_toint(const float *x, void *q, int out_bits, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     if (qmin > qmax) return (int)cudaErrorInvalidValue;
     if (!toint_bits_ok(out_bits)) return (int)cudaErrorInvalidValue;
+    if (rounding == RND_HALF_EVEN) {
+        if (out_bits == 8) return launch_channel<LinearOp<0>, int8_t>(x, (int8_t *)q, n, epc, C, scale, offset, {qmin, qmax, 0}, st);
+        return launch_channel<LinearOp<0>, int32_t>(x, (int32_t *)q, n, epc, C, scale, offset, {qmin, qmax, 0}, st);
+    }
     if (out_bits == 8) return launch_channel<LinearOp<-1>, int8_t>(x, (int8_t *)q, n, epc, C, scale, offset, {qmin, qmax, rounding}, st);
     return launch_channel<LinearOp<-1>, int32_t>(x, (int32_t *)q, n, epc, C, scale, offset, {qmin, qmax, rounding}, st);
 }
@@ -506,6 +606,7 @@ int ppq_b200_multi_linear_quant_c(const ppq_b200_lc_desc *descs, int count, int6
     if (g > (int64_t)sm_count() * 8) g = (int64_t)sm_count() * 8;
     const size_t smem = (size_t)(count + 1) * sizeof(long long);
     if (rounding == RND_HALF_EVEN) multi_channel_kernel<LinearOp<0>><<<(int)g, kThreads, smem, (cudaStream_t)stream>>>(descs, count, {qmin, qmax, 0});
+    else if (rounding == RND_HALF_UP) multi_channel_kernel<LinearOp<RND_HALF_UP>><<<(int)g, kThreads, smem, (cudaStream_t)stream>>>(descs, count, {qmin, qmax, RND_HALF_UP});
     else multi_channel_kernel<LinearOp<-1>><<<(int)g, kThreads, smem, (cudaStream_t)stream>>>(descs, count, {qmin, qmax, rounding});
     return (int)cudaGetLastError();
 }
@@ -514,11 +615,10 @@ int ppq_b200_float_quant_t(const float *x, float *y, int64_t n, const float *sca
                            int exponent, int mantissa, float clip_min, float clip_max, int rounding, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!valid_fp_format(exponent, mantissa)) return (int)cudaErrorInvalidValue;
-    if (rounding == RND_HALF_EVEN) {
-        if (float_fast_path_ok(exponent, mantissa, clip_min, clip_max))
-            return launch_tensor<FloatOp<0, true>, float>(x, y, n, scale, offset, {exponent, mantissa, 0, clip_min, clip_max}, st);
-        return launch_tensor<FloatOp<0>, float>(x, y, n, scale, offset, {exponent, mantissa, 0, clip_min, clip_max}, st);
+    if (float_fast_path_ok(exponent, mantissa, clip_min, clip_max)) {
+        PPQB_DISPATCH_MODE(rounding, return (launch_tensor<FloatOp<M_, true>, float>(x, y, n, scale, offset, {exponent, mantissa, M_, clip_min, clip_max}, st)))
     }
+    if (rounding == RND_HALF_EVEN) return launch_tensor<FloatOp<0>, float>(x, y, n, scale, offset, {exponent, mantissa, 0, clip_min, clip_max}, st);
     return launch_tensor<FloatOp<-1>, float>(x, y, n, scale, offset, {exponent, mantissa, rounding, clip_min, clip_max}, st);
 }
 
@@ -526,11 +626,10 @@ int ppq_b200_float_quant_c(const float *x, float *y, int64_t n, int64_t epc, int
                            int exponent, int mantissa, float clip_min, float clip_max, int rounding, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!valid_fp_format(exponent, mantissa)) return (int)cudaErrorInvalidValue;
-    if (rounding == RND_HALF_EVEN) {
-        if (float_fast_path_ok(exponent, mantissa, clip_min, clip_max))
-            return launch_channel<FloatOp<0, true>, float>(x, y, n, epc, C, scale, offset, {exponent, mantissa, 0, clip_min, clip_max}, st);
-        return launch_channel<FloatOp<0>, float>(x, y, n, epc, C, scale, offset, {exponent, mantissa, 0, clip_min, clip_max}, st);
+    if (float_fast_path_ok(exponent, mantissa, clip_min, clip_max)) {
+        PPQB_DISPATCH_MODE(rounding, return (launch_channel<FloatOp<M_, true>, float>(x, y, n, epc, C, scale, offset, {exponent, mantissa, M_, clip_min, clip_max}, st)))
     }
+    if (rounding == RND_HALF_EVEN) return launch_channel<FloatOp<0>, float>(x, y, n, epc, C, scale, offset, {exponent, mantissa, 0, clip_min, clip_max}, st);
     return launch_channel<FloatOp<-1>, float>(x, y, n, epc, C, scale, offset, {exponent, mantissa, rounding, clip_min, clip_max}, st);
 }
 

@@ -16,6 +16,7 @@ static int key_of(const char *name) {
     if (!strcmp(name, "linear_quant_t")) return kVarLinearT;
     if (!strcmp(name, "histogram")) return kVarHistogram;
     if (!strcmp(name, "minmax")) return kVarMinMax;
+    if (!strcmp(name, "linear_quant_c")) return kVarChannel;
     return -1;
 }
 }  // namespace ppqb

@@ -30,6 +30,12 @@ struct LinearOp {
         o = offset_to_int(off);
     }
     __device__ __forceinline__ void rebind(float s, float off) { d.init(s); o = offset_to_int(off); }     // same plan, next channel
+    // the per-channel part of the operator as a 16-byte shared-memory table entry (built once per row of a tile, see ew_channel_table_kernel)
+    static __device__ __forceinline__ float4 entry(float s, float off) {
+        ExactDiv e(s);
+        return make_float4(e.s, e.r, __int_as_float(offset_to_int(off)), 0.f);
+    }
+    __device__ __forceinline__ LinearOp(const Plan &p, const float4 &e) : lo(p.lo), hi(p.hi), mode(p.mode) { d.s = e.x; d.r = e.y; o = __float_as_int(e.z); }
     __device__ __forceinline__ int finish(float t) const {
         int q;
         if constexpr (MODE >= 0) q = round2int<MODE>(t); else q = round2int_dyn(t, mode);
@@ -57,16 +63,19 @@ struct LinearOp {
     }
 };
 
-// FAST (HALF_EVEN only, chosen on the host by float_fast_path_ok): the branch-free path, valid when both saturation bounds are
+// FAST (compile-time MODE, chosen on the host by float_fast_path_ok): the branch-free path, valid when both saturation bounds are
 // fixed points of the rounding (lie on the FP(E,M) grid), so that round(clamp(u)) equals the reference's early returns and its
-// final CLIP is a no-op.
+// final CLIP is a no-op.  In the normal range the reference rounds the DISCARDED mantissa bits, taken as a fraction in [0, 1), with
+// _round2int (common.cuh:218-222): the fraction is never negative, so every policy reduces to "carry iff d > half" (HALF_EVEN -- rint(0.5)
+// == 0 --, HALF_DOWN, HALF_TOWARDS_ZERO), "carry iff d >= half" (HALF_UP, HALF_FAR_FROM_ZERO, TO_NEAR_INT), "carry iff d > 0" (UP) or
+// "never" (DOWN): one integer add of a per-mode constant and a mask.  The sub-normal grid rounds the SIGNED quotient with the policy itself.
 template <int MODE, bool FAST = false>
 struct FloatOp {
     struct Params { int E, M, mode; float cmin, cmax; };
     static constexpr bool kLight = FAST;
     struct Plan {
         float hi, lo, cmin, cmax, min_sub, inv_min_sub, sub_magic, sub_thresh;
-        uint32_t sub_thresh_bits, half_minus1, keep_mask; int M, mode;
+        uint32_t sub_thresh_bits, half_minus1, keep_mask, carry_add; int M, mode;
         __device__ __forceinline__ explicit Plan(const Params &p) : cmin(p.cmin), cmax(p.cmax), M(p.M), mode(p.mode) {
             const int emin = -(1 << (p.E - 1)) + 1, emax = 1 << (p.E - 1);
             const uint32_t top = ~(0x007FFFFFu >> p.M) & 0x007FFFFFu;
@@ -81,11 +90,16 @@ struct FloatOp {
             sub_thresh = __uint_as_float(sub_thresh_bits);
             half_minus1 = (1u << (22 - p.M)) - 1u;
             keep_mask = ~((1u << (23 - p.M)) - 1u);
+            constexpr int m = MODE;
+            carry_add = (m == RND_HALF_UP || m == RND_HALF_FAR_FROM_ZERO || m == RND_TO_NEAR_INT) ? (1u << (22 - p.M))
+                      : (m == RND_UP ? (1u << (23 - p.M)) - 1u : (m == RND_DOWN ? 0u : half_minus1));
         }
     };
     const Plan &pl; ExactDiv d; float off;
     __device__ __forceinline__ FloatOp(const Plan &p, float s, float o) : pl(p), off(o) { d.init(s); }
     __device__ __forceinline__ void rebind(float s, float o) { d.init(s); off = o; }
+    static __device__ __forceinline__ float4 entry(float s, float o) { ExactDiv e(s); return make_float4(e.s, e.r, o, 0.f); }
+    __device__ __forceinline__ FloatOp(const Plan &p, const float4 &e) : pl(p), off(e.z) { d.s = e.x; d.r = e.y; }
     static constexpr float kDivLimit = 1.15e18f;                                        // ~2^60: beyond this use div.rn
     // u = x / s already computed exactly; returns the value on the FP(E,M) grid
     __device__ __forceinline__ float grid(float u) const {
@@ -96,10 +110,12 @@ struct FloatOp {
                 // because rint(0.5) == 0 upstream); the carry may bump the exponent.  Adding to the signed pattern is the same as
                 // adding to the magnitude: a clamped finite value cannot carry into bit 31, and the canonical NaN has sign 0
                 // (its carry into bit 31 reproduces the reference's -0.0 for NaN).
-                const uint32_t nb = (__float_as_uint(uc) + pl.half_minus1) & pl.keep_mask;
+                const uint32_t nb = (__float_as_uint(uc) + pl.carry_add) & pl.keep_mask;
                 // subnormal range: ties-to-even on the 2^-k grid, computed with the add-magic-constant trick (sign of zero lost,
-                // exactly like the int round trip upstream)
-                const float sub = __fsub_rn(__fadd_rn(uc, pl.sub_magic), pl.sub_magic);
+                // exactly like the int round trip upstream); the other policies round the signed quotient with the policy itself
+                float sub;
+                if constexpr (MODE == RND_HALF_EVEN) sub = __fsub_rn(__fadd_rn(uc, pl.sub_magic), pl.sub_magic);
+                else sub = __fmul_rn(__int2float_rn(round2int<MODE>(__fmul_rn(uc, pl.inv_min_sub))), pl.min_sub);
                 return fabsf(uc) < pl.sub_thresh ? sub : __uint_as_float(nb);            // false for NaN -> nb, as with the integer compare
             }
         }

@@ -4,8 +4,9 @@
 //   "histogram":      0 default (1024-thr CTA per SM, unconditional red.shared + trash slot) | 1 generic-pointer atomicAdd
 //                     | 2 __match_any_sync aggregation | 3 global atomics like the reference | 4 the first layout (256-thr CTAs x 8 per SM)
 //                     | 5, 6 two 1024-thr CTAs per SM (32 registers), 2 / 4 loads in flight
+//   "linear_quant_c": 0 default (shared-memory operator table for rows shorter than 512 elements) | 1 the round-1 per-vector operator rebuild
 #pragma once
 namespace ppqb {
-enum { kVarLinearT = 0, kVarHistogram = 1, kVarMinMax = 2, kVarCount = 8 };
+enum { kVarLinearT = 0, kVarHistogram = 1, kVarMinMax = 2, kVarChannel = 3, kVarCount = 8 };
 int variant_of(int key);
 }
