@@ -79,6 +79,19 @@ typedef struct {
 PPQ_B200_API int ppq_b200_multi_linear_quant_c(const ppq_b200_lc_desc *descs, int count, int64_t max_n,
                                                int qmin, int qmax, int rounding, void *stream);
 
+/* QuantizeTensor_LT (linear.cu:88-130) for a table of tensors in ONE launch, each with its own (scale, offset): the per-tensor
+ * activation configs of a quantised graph (executor/torch.py:516-518, 541-543 call the op ~100x per forward on tensors of a few hundred KB,
+ * where a launch costs more than the kernel).  One descriptor per tensor, in DEVICE memory. */
+typedef struct {
+    const float *x;        /* input  (borrowed) */
+    float       *y;        /* output (caller-allocated, may not alias x) */
+    const float *scale;    /* [1] */
+    const float *offset;   /* [1] */
+    int64_t      n;        /* elements */
+} ppq_b200_lt_desc;
+PPQ_B200_API int ppq_b200_multi_linear_quant_t(const ppq_b200_lt_desc *descs, int count, int64_t max_n,
+                                               int qmin, int qmax, int rounding, void *stream);
+
 /* ---- low-precision float fake-quant (FP8 E4M3 default; E in 1..5 and 2^(E-1)+M-2 in 0..30: E4M3, E5M2, E5M10 ...) --------------- */
 /* replaces QuantizeTensor_FT, ppq/csrc/cuda/floating.cu:36-75 with QuantizeScalarFloating,
  * common.cuh:154-226 (ffi.py:272-288 CUDA.FloatingQuantize_T).  Reference tie rule kept (ties toward zero in the

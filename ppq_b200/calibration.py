@@ -416,29 +416,31 @@ class RuntimeCalibrationPass:
 
 
 class MultiWeightQuantizer:
-    """All per-channel weights of a network (or, with channel_axis=None, any list of per-tensor quantised tensors) fake-quantised by
-    ONE launch (Multi_QuantizeTensor_LC).  The executor re-quantises
+    """All per-channel weights of a network fake-quantised by ONE launch (Multi_QuantizeTensor_LC), or -- with channel_axis=None -- any list
+    of per-tensor quantised tensors, each with its own (scale, offset), by ONE Multi_QuantizeTensor_LT launch.  The executor re-quantises
     every Conv/Gemm weight on each forward until ParameterBakingPass freezes them (executor/torch.py:516-518); with ~54 small
     tensors per ResNet-50 forward that is launch-latency, not bandwidth -- one descriptor table turns it into one kernel."""
 
     def __init__(self, weights: Sequence[torch.Tensor], scales: Sequence[torch.Tensor], offsets: Sequence[torch.Tensor],
-                 channel_axis: int = 0, quant_min: int = -128, quant_max: int = 127, rounding: int = 0):
+                 channel_axis: Optional[int] = 0, quant_min: int = -128, quant_max: int = 127, rounding: int = 0):
         from .ffi import extension
         self.ext = extension()
         self.quant_min, self.quant_max, self.rounding = quant_min, quant_max, rounding
+        self.per_tensor = channel_axis is None
         self.weights = [w.contiguous() for w in weights]
         self.outputs = [torch.empty_like(w) for w in self.weights]
         self.scales = [s.contiguous() for s in scales]
         self.offsets = [o.contiguous() for o in offsets]
         rows = []
         for w, y, s, o in zip(self.weights, self.outputs, self.scales, self.offsets):
-            if channel_axis is None:                       # per-tensor: one channel spanning the whole tensor
-                epc, C = w.numel(), 1
-            else:
-                axis = channel_axis % w.dim()
-                epc = 1
-                for d in w.shape[axis + 1:]: epc *= int(d)
-                C = int(w.shape[axis])
+            if self.per_tensor:
+                assert s.numel() == 1 and o.numel() == 1
+                rows.append([w.data_ptr(), y.data_ptr(), s.data_ptr(), o.data_ptr(), w.numel()])
+                continue
+            axis = channel_axis % w.dim()
+            epc = 1
+            for d in w.shape[axis + 1:]: epc *= int(d)
+            C = int(w.shape[axis])
             assert s.numel() == C and o.numel() == C
             rows.append([w.data_ptr(), y.data_ptr(), s.data_ptr(), o.data_ptr(), w.numel(), epc, C])
         self.max_n = max(r[4] for r in rows)
@@ -448,6 +450,7 @@ class MultiWeightQuantizer:
 
     @torch.no_grad()
     def __call__(self) -> List[torch.Tensor]:
+        launch = self.ext.Multi_QuantizeTensor_LT if self.per_tensor else self.ext.Multi_QuantizeTensor_LC
         for table in self._tables:
-            self.ext.Multi_QuantizeTensor_LC(table, self.max_n, self.quant_min, self.quant_max, self.rounding)
+            launch(table, self.max_n, self.quant_min, self.quant_max, self.rounding)
         return self.outputs

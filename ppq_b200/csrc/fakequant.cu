@@ -422,6 +422,62 @@ multi_channel_kernel(const ppq_b200_lc_desc *__restrict__ descs, int count, type
     }
 }
 
+// ---- multi-tensor per-tensor fake-quant: the activation tensors of a quantised graph in ONE launch -----------------------------------------
+// Same partition as multi_channel_kernel (512-element warp segments, the concatenation of all segments split evenly over the CTAs), but one
+// operator per tensor: it is built once per (CTA, tensor) visit and the loop body is the per-tensor kernel's.
+template <class Op>
+__global__ void __launch_bounds__(kThreads)
+multi_tensor_kernel(const ppq_b200_lt_desc *__restrict__ descs, int count, typename Op::Params p) {
+    extern __shared__ long long seg_prefix[];                          // [count + 1], in segments
+    for (int t = threadIdx.x; t < count; t += kThreads) {
+        const int64_t n = descs[t].n;
+        seg_prefix[t + 1] = n > 0 ? (n + 4 * kSegVec - 1) / (4 * kSegVec) : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long run = 0; seg_prefix[0] = 0;
+        for (int t = 1; t <= count; t++) { run += seg_prefix[t]; seg_prefix[t] = run; }
+    }
+    __syncthreads();
+    const int64_t total = seg_prefix[count];
+    const int64_t span = (total + gridDim.x - 1) / gridDim.x;
+    const int64_t s0 = (int64_t)blockIdx.x * span, s1 = (s0 + span) < total ? (s0 + span) : total;
+    if (s0 >= total) return;
+    int t;
+    { int lo = 0, hi = count - 1; while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (seg_prefix[mid] <= s0) lo = mid; else hi = mid - 1; } t = lo; }
+    const typename Op::Plan plan(p);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (; t < count && seg_prefix[t] < s1; t++) {
+        const int64_t first = seg_prefix[t], segs = seg_prefix[t + 1] - first;
+        if (segs == 0) continue;
+        const ppq_b200_lt_desc d = descs[t];
+        const uint32_t a = (uint32_t)(s0 > first ? s0 - first : 0), b = (uint32_t)((s1 - first) < segs ? (s1 - first) : segs);
+        const Op op(plan, __ldg(d.scale), __ldg(d.offset));
+        const uint32_t n = (uint32_t)d.n;
+        if (((reinterpret_cast<uintptr_t>(d.x) | reinterpret_cast<uintptr_t>(d.y)) & 15u) == 0) {
+            const uint32_t n4 = n >> 2;
+            const float4 *x4 = reinterpret_cast<const float4 *>(d.x);
+            for (uint32_t sg = a + warp; sg < b; sg += kThreads / 32) {
+                const uint32_t base = sg * kSegVec + lane;
+                float4 v[kUnroll];
+#pragma unroll
+                for (int j = 0; j < kUnroll; j++) if (base + j * 32 < n4) v[j] = ld_stream4(x4 + base + j * 32);
+#pragma unroll
+                for (int j = 0; j < kUnroll; j++) if (base + j * 32 < n4) Emit<Op, float>::vec(op, v[j], d.y, (int64_t)(base + j * 32));
+                if (sg == (uint32_t)segs - 1) {                          // <= 3 elements after the last whole vector
+                    const uint32_t e = (n4 << 2) + lane;
+                    if (e < n) d.y[e] = op.apply(ld_stream1(d.x + e));
+                }
+            }
+        } else {
+            for (uint32_t sg = a + warp; sg < b; sg += kThreads / 32) {
+                const uint32_t e0 = sg * (4 * kSegVec);
+                for (uint32_t e = e0 + lane; e < min(n, e0 + 4 * kSegVec); e += 32) d.y[e] = op.apply(ld_stream1(d.x + e));
+            }
+        }
+    }
+}
+
 // ---- host-side launch helpers --------------------------------------------------------------------------------------------
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 template <class OutT> static inline bool out_aligned(const void *p) {
@@ -529,16 +585,16 @@ extern "C" {
 
 // Every rounding policy is a compile-time instantiation behind one switch (the run-time-mode operator, LinearOp<-1>, costs 20 points of
 // HBM peak: its uniform branches and the fp32 "+ .5" forms of all four half-way modes stay live in the loop).
-#define PPQB_DISPATCH_MODE(rounding, CALL)                          \
+#define PPQB_DISPATCH_MODE(rounding, ...)                           \
     switch (rounding) {                                             \
-    case RND_HALF_EVEN:          { constexpr int M_ = RND_HALF_EVEN; CALL; }          \
-    case RND_HALF_UP:            { constexpr int M_ = RND_HALF_UP; CALL; }            \
-    case RND_HALF_DOWN:          { constexpr int M_ = RND_HALF_DOWN; CALL; }          \
-    case RND_HALF_TOWARDS_ZERO:  { constexpr int M_ = RND_HALF_TOWARDS_ZERO; CALL; }  \
-    case RND_HALF_FAR_FROM_ZERO: { constexpr int M_ = RND_HALF_FAR_FROM_ZERO; CALL; } \
-    case RND_TO_NEAR_INT:        { constexpr int M_ = RND_TO_NEAR_INT; CALL; }        \
-    case RND_UP:                 { constexpr int M_ = RND_UP; CALL; }                 \
-    case RND_DOWN:               { constexpr int M_ = RND_DOWN; CALL; }               \
+    case RND_HALF_EVEN:          { constexpr int M_ = RND_HALF_EVEN; __VA_ARGS__; }          \
+    case RND_HALF_UP:            { constexpr int M_ = RND_HALF_UP; __VA_ARGS__; }            \
+    case RND_HALF_DOWN:          { constexpr int M_ = RND_HALF_DOWN; __VA_ARGS__; }          \
+    case RND_HALF_TOWARDS_ZERO:  { constexpr int M_ = RND_HALF_TOWARDS_ZERO; __VA_ARGS__; }  \
+    case RND_HALF_FAR_FROM_ZERO: { constexpr int M_ = RND_HALF_FAR_FROM_ZERO; __VA_ARGS__; } \
+    case RND_TO_NEAR_INT:        { constexpr int M_ = RND_TO_NEAR_INT; __VA_ARGS__; }        \
+    case RND_UP:                 { constexpr int M_ = RND_UP; __VA_ARGS__; }                 \
+    case RND_DOWN:               { constexpr int M_ = RND_DOWN; __VA_ARGS__; }               \
     default: break;                                                 \
     }
 
@@ -608,6 +664,17 @@ int ppq_b200_multi_linear_quant_c(const ppq_b200_lc_desc *descs, int count, int6
     if (rounding == RND_HALF_EVEN) multi_channel_kernel<LinearOp<0>><<<(int)g, kThreads, smem, (cudaStream_t)stream>>>(descs, count, {qmin, qmax, 0});
     else if (rounding == RND_HALF_UP) multi_channel_kernel<LinearOp<RND_HALF_UP>><<<(int)g, kThreads, smem, (cudaStream_t)stream>>>(descs, count, {qmin, qmax, RND_HALF_UP});
     else multi_channel_kernel<LinearOp<-1>><<<(int)g, kThreads, smem, (cudaStream_t)stream>>>(descs, count, {qmin, qmax, rounding});
+    return (int)cudaGetLastError();
+}
+
+int ppq_b200_multi_linear_quant_t(const ppq_b200_lt_desc *descs, int count, int64_t max_n, int qmin, int qmax, int rounding, void *stream) {
+    if (count <= 0 || count > kMaxMultiTensors || max_n <= 0 || max_n > 0x7fffffffLL || !descs || qmin > qmax) return (int)cudaErrorInvalidValue;
+    int64_t g = ((int64_t)count * ((max_n + 4 * kSegVec - 1) / (4 * kSegVec)) + 7) / 8;      // upper bound: one CTA per 8 segments, at most 8 CTAs per SM
+    if (g > (int64_t)sm_count() * 8) g = (int64_t)sm_count() * 8;
+    const size_t smem = (size_t)(count + 1) * sizeof(long long);
+    cudaStream_t st = (cudaStream_t)stream;
+    PPQB_DISPATCH_MODE(rounding, { multi_tensor_kernel<LinearOp<M_>><<<(int)g, kThreads, smem, st>>>(descs, count, {qmin, qmax, M_}); return (int)cudaGetLastError(); })
+    multi_tensor_kernel<LinearOp<-1>><<<(int)g, kThreads, smem, st>>>(descs, count, {qmin, qmax, rounding});
     return (int)cudaGetLastError();
 }
 

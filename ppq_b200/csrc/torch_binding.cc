@@ -286,6 +286,14 @@ void Multi_QuantizeTensor_LC(const Tensor &descs, const int64_t max_numel, const
     CheckStatus(ppq_b200_multi_linear_quant_c(reinterpret_cast<const ppq_b200_lc_desc *>(descs.data_ptr<int64_t>()), (int)descs.size(0), max_numel,
                                               clip_min, clip_max, rounding, Stream()), "Multi_QuantizeTensor_LC");
 }
+// descs: int64 tensor [count, 5] on the device = (x, y, scale, offset, numel) -- bit-compatible with ppq_b200_lt_desc
+void Multi_QuantizeTensor_LT(const Tensor &descs, const int64_t max_numel, const int clip_min, const int clip_max, const int rounding) {
+    CheckTensor(descs, at::kLong, "Descriptors(Expect to be INT64)");
+    if (descs.dim() != 2 || descs.size(1) != 5 || !descs.is_contiguous()) throw KernelFailure("Kernel Failure, descriptor table must be [count, 5] int64.");
+    const c10::cuda::CUDAGuard guard(descs.device());
+    CheckStatus(ppq_b200_multi_linear_quant_t(reinterpret_cast<const ppq_b200_lt_desc *>(descs.data_ptr<int64_t>()), (int)descs.size(0), max_numel,
+                                              clip_min, clip_max, rounding, Stream()), "Multi_QuantizeTensor_LT");
+}
 std::vector<Tensor> MSE_Search(const Tensor &hist_arena, const int64_t bins, const Tensor &minmax_arena, const int quant_min, const int quant_max,
                                const bool symmetrical, const bool power_of_2, const double min_scale, const int interval) {
     CheckTensor(hist_arena, at::kInt, "HistArena(Expect to be INT32)");
@@ -319,6 +327,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     // B200-native extras
     m.def("QuantizeTensor_toInt", QuantizeTensor_toInt, "QuantizeTensor_toInt");
     m.def("Multi_QuantizeTensor_LC", Multi_QuantizeTensor_LC, "Multi_QuantizeTensor_LC");
+    m.def("Multi_QuantizeTensor_LT", Multi_QuantizeTensor_LT, "Multi_QuantizeTensor_LT");
     m.def("MinMax_Init", MinMax_Init, "MinMax_Init");
     m.def("MinMax_T", MinMax_T, "MinMax_T");
     m.def("MinMax_C", MinMax_C, "MinMax_C");

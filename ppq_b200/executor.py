@@ -496,35 +496,70 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
 
 
 @torch.no_grad()
-def graphwise_error_analyse(executor: TorchExecutor, batches, to_device=None) -> Dict[str, float]:
+def graphwise_error_analyse(executor: TorchExecutor, batches, to_device=None, graphs: bool = False) -> Dict[str, float]:
     """The evaluation loop where fake-quant throughput shows up in user wall-clock (ppq/quantization/analyse/graphwise.py:64-183): run every batch
     through the network twice -- all configs dequantised (fp32) and all configs active -- and report, per quantable operation, the SNR
     mean((q - f)^2) / mean(f^2) per sample, averaged (torch_snr_error, ppq/quantization/measure/norm.py:52-93).  Every activation goes through
-    QuantizeTensor_LT and every weight through the multi-tensor QuantizeTensor_LC on each quantised forward."""
-    from .core import set_state
+    QuantizeTensor_LT and every weight through the multi-tensor QuantizeTensor_LC on each quantised forward.
+    graphs=True captures the fp32 forward and the quantised forward (network kernels + ~100 small fake-quant launches + the hooks' bookkeeping)
+    into two CUDA graphs on the first batch and replays them for the others (fixed batch shape): the per-call host cost of the drop-in flow
+    (python -> binding -> allocator -> launch, 4.5-5 us x every config x every forward) disappears from the loop."""
     cfgs = executor.observed_configs_all() + [op.weight_cfg for _, op in executor.quantable_operations() if op.weight_cfg is not None]
     saved = [c.state for c in cfgs]
     names = [n for n, op in executor.quantable_operations()]
-    acc = {n: [0.0, 0] for n in names}
+    acc = {n: None for n in names}
+    count = 0
 
     class Tap:
         def __init__(self, name, store): self.name, self.store = name, store
         def pre_forward_hook(self, **kw): pass
         def post_forward_hook(self, outputs, quant_outputs, quant_configs): self.store[self.name] = quant_outputs[0]
 
-    for x in batches:
-        if to_device is not None: x = to_device(x)
-        fp, qt = {}, {}
-        for c in cfgs: c.state = type(c.state)['FP32'] if getattr(c.state, 'name', '') in ('ACTIVATED', 'PASSIVE') else c.state
-        executor.forward(x, hooks={n: Tap(n, fp) for n in names})
-        for c, st in zip(cfgs, saved): c.state = st
-        executor.forward(x, hooks={n: Tap(n, qt) for n in names})
-        for n in names:
-            f, q = fp[n].flatten(1), qt[n].flatten(1)
-            snr = (torch.pow(q - f, 2).sum(dim=-1) / (torch.pow(f, 2).sum(dim=-1) + 1e-7)).mean()
-            acc[n][0] += float(snr); acc[n][1] += 1
-    for c, st in zip(cfgs, saved): c.state = st
-    return {n: v[0] / max(v[1], 1) for n, v in acc.items()}
+    def dequantised(flag: bool):
+        for c, st in zip(cfgs, saved):
+            c.state = type(c.state)['FP32'] if (flag and getattr(st, 'name', '') in ('ACTIVATED', 'PASSIVE')) else st
+
+    def both(x, fp, qt):
+        dequantised(True); executor.forward(x, hooks={n: Tap(n, fp) for n in names})
+        dequantised(False); executor.forward(x, hooks={n: Tap(n, qt) for n in names})
+
+    def snr_all(fp, qt):
+        return torch.stack([(torch.pow(qt[n].flatten(1) - fp[n].flatten(1), 2).sum(dim=-1) / (torch.pow(fp[n].flatten(1), 2).sum(dim=-1) + 1e-7)).mean()
+                            for n in names])
+
+    static_in, graph, fp, qt, static_snr = None, None, {}, {}, None
+    try:
+        for x in batches:
+            if to_device is not None: x = to_device(x)
+            if not graphs:
+                fp, qt = {}, {}
+                both(x, fp, qt)
+                snr = snr_all(fp, qt)
+            else:
+                if graph is None:
+                    static_in = x.clone()
+                    dev = static_in.device
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):                         # eager first: lazy initialisation (descriptor tables, cuDNN plans)
+                        both(static_in, {}, {})
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        both(static_in, fp, qt)
+                        static_snr = snr_all(fp, qt)
+                else:
+                    static_in.copy_(x, non_blocking=True)
+                graph.replay()
+                snr = static_snr.clone()
+            acc_t = snr if count == 0 else acc_t + snr                     # noqa: F821 (defined on the first iteration)
+            count += 1
+    finally:
+        dequantised(False)
+    if count == 0: return {n: 0.0 for n in names}
+    vals = (acc_t / count).tolist()
+    del acc
+    return dict(zip(names, vals))
 
 
 def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int, device, world: int = 1, seed: int = 0, graphs: bool = False):

@@ -1,5 +1,7 @@
 """BASELINE.json configs 3-5 as parity cases (config 1 is in test_gpu_parity.py, config 2 is bench.py's workload), plus the host-side
 pieces of the path that sit above the kernels: FP8 observers, dynamic quantisation, the module executor and the calibration drivers."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -138,7 +140,8 @@ def test_dynamic_quantization_on_device(ext, oracle):
 
 def test_executor_calibration_paths_agree(ext):
     """The module executor: hook-driven RuntimeCalibrationPass (one observer per tensor, the reference flow) and the arena calibrator (immediate
-    and deferred multi-tensor) give identical scales; weights are re-quantised per forward; baked weights equal the fake-quantised ones."""
+    and deferred multi-tensor) give identical scales; weights are re-quantised per forward.  (Parity of the same flows with the REAL reference
+    pipeline, incl. alignment and baked weights: tests/test_gpu_graph_parity.py.)"""
     import torchvision
     from ppq_b200.calibration import RuntimeCalibrationPass
     from ppq_b200.core import QuantizationStates
@@ -170,8 +173,13 @@ def test_executor_calibration_paths_agree(ext):
     report = graphwise_error_analyse(ex2, data[:2])
     assert len(report) == len(ex2.quantable_operations()) and all(0 <= v < 0.1 for v in report.values()), max(report.values())
     assert all(c.state == QuantizationStates.ACTIVATED for c in ex2.observed_configs_all())       # states restored
+    if os.environ.get('PYTORCH_NO_CUDA_MEMORY_CACHING') != '1':
+        report_g = graphwise_error_analyse(ex2, data[:3], graphs=True)     # both forwards captured in CUDA graphs, replayed per batch
+        report_e = graphwise_error_analyse(ex2, data[:3])
+        assert report_g.keys() == report_e.keys() and all(abs(report_g[k] - report_e[k]) <= 1e-6 + 1e-4 * abs(report_e[k]) for k in report_e), \
+            max(abs(report_g[k] - report_e[k]) for k in report_e)
+        assert all(c.state == QuantizationStates.ACTIVATED for c in ex2.observed_configs_all())
     # CUDA-graph replay of the whole forward (network + weight fake-quant + collectors): identical statistics
-    import os
     if os.environ.get('PYTORCH_NO_CUDA_MEMORY_CACHING') != '1':            # capture needs torch's caching allocator (tools/gpu_sanitize.sh turns it off)
         ex3 = build()
         cal3 = calibrate_arena(ex3, data, method='kl', graphs=True)

@@ -172,3 +172,30 @@ def test_gpu_pipeline_agrees_with_the_cpu_path_fixture(env, method):
         else:
             np.testing.assert_allclose(g['scale'], z[r['scale']], rtol=2e-3 if method == 'percentile' else 1e-4)
     np.testing.assert_allclose(got['output'], z[f'{method}.output'], atol=0.08)           # a few quantisation steps of the last layer
+
+
+def test_parameter_baking_states_values_and_no_requantisation(env):
+    """ParameterBakingPass semantics (ppq/IR/quantize.py:98-111, optim/baking.py:34-47): ACTIVATED -> BAKED, PASSIVE -> PASSIVE_BAKED, the
+    baked value IS the fake-quantised value, and later forwards use it as is (no weight fake-quant launch, the parameter is not touched)."""
+    from ppq_b200.core import QuantizationStates as S
+    from ppq_b200.qfunction import PPQuantFunction
+    ex, batches = our_executor(env)
+    ops = dict(ex.quantable_operations())
+    ops['conv3#0'].weight_cfg.master_by = ops['conv2#0'].weight_cfg        # a passive parameter config: shares conv2's per-channel scales (16 channels each)
+    assert ops['conv3#0'].weight_cfg.state == S.PASSIVE and ops['conv3#0'].weight_cfg.scale is ops['conv2#0'].weight_cfg.scale
+    weighted = {n: op for n, op in ops.items() if op.weight_cfg is not None}
+    want = {n: PPQuantFunction(op.module.weight.data, op.weight_cfg).clone() for n, op in weighted.items()}
+    assert len(ex._quantize_all_weights()) == len(weighted) - 1            # before baking: every ACTIVATED weight is re-quantised per forward (one launch)
+    ex._restore_weights()
+    ex.bake_parameters()
+    for n, op in weighted.items():
+        assert op.weight_cfg.state == (S.PASSIVE_BAKED if n == 'conv3#0' else S.BAKED), (n, op.weight_cfg.state)
+        assert np.array_equal(bits(op.module.weight.data.cpu().numpy()), bits(want[n].cpu().numpy())), n
+    assert ex._quantize_all_weights() == {}                                # nothing left to quantise per forward
+    ptrs = {n: op.module.weight.data_ptr() for n, op in weighted.items()}
+    ex.forward(batches[0])
+    for n, op in weighted.items():
+        assert op.module.weight.data_ptr() == ptrs[n] and np.array_equal(bits(op.module.weight.data.cpu().numpy()), bits(want[n].cpu().numpy())), n
+    ex.bake_parameters()                                                   # idempotent: BAKED configs are skipped
+    for n, op in weighted.items():
+        assert np.array_equal(bits(op.module.weight.data.cpu().numpy()), bits(want[n].cpu().numpy())), n

@@ -284,6 +284,23 @@ def test_multi_tensor_lc_matches_single_launches(ext, oracle):
         assert_bits_equal(y, oracle.linear_quant_c(w.cpu().numpy(), s.cpu().numpy(), o.cpu().numpy(), 0, -8, 7, 4), 'int4 mode 4 ' + str(tuple(w.shape)))
 
 
+def test_multi_tensor_lt_matches_single_launches(ext, oracle):
+    """Multi_QuantizeTensor_LT: the per-tensor activation configs of a graph in one launch, each tensor with its OWN scale and offset (ragged
+    sizes, a tensor of 1 element, a tail of 1..3 elements after the last vector, an unaligned view), all rounding modes."""
+    from ppq_b200.calibration import MultiWeightQuantizer
+    r = np.random.RandomState(78)
+    sizes = [401408, 150528, 1, 3, 4099, 1000, 513, 512, 7, 25088 * 3 + 2]
+    xs = [dev((r.standard_normal(n) * (1 + i)).astype(np.float32)) for i, n in enumerate(sizes)]
+    xs[4] = dev(np.concatenate([np.zeros(1, np.float32), xs[4].cpu().numpy()]))[1:]                        # not 16-byte aligned
+    scales = [dev(np.float32([0.01 * (i + 1)])) for i in range(len(xs))]
+    offsets = [dev(np.float32([float(i % 5)])) for i in range(len(xs))]
+    for mode in range(8):
+        outs = MultiWeightQuantizer(xs, scales, offsets, channel_axis=None, quant_min=-100, quant_max=120, rounding=mode)()
+        for x, s_, o_, y in zip(xs, scales, offsets, outs):
+            assert torch.equal(y, ext.QuantizeTensor_LT(x, s_, o_, -100, 120, mode)), (mode, x.numel())
+            assert_bits_equal(y, oracle.linear_quant_t(x.cpu().numpy(), float(s_.item()), float(o_.item()), -100, 120, mode), f'mode {mode} n {x.numel()}')
+
+
 # ------------------------------------------------------------------------------------------------ FP8 & friends
 FP_FORMATS = [(4, 3, -448.0, 448.0), (5, 2, -57344.0, 57344.0), (4, 3, -240.0, 240.0), (5, 10, -65504.0, 65504.0), (3, 4, -30.0, 30.0),
               (2, 1, -6.0, 6.0)]
