@@ -9,13 +9,16 @@
 //
 // All of them read each element exactly once (4 B/element algorithmic traffic) with 128-bit streaming loads, four per
 // thread in flight.  Histograms are privatised per CTA in shared memory (bins x int32, 16 KB for the KL observer's 4096
-// bins), the post-ReLU hot spot (bin 0) is counted with a warp ballot instead of 32-way same-address atomics, and only
-// non-empty bins are flushed to the caller's global histogram with red.global.add.
+// bins) and counted with an unconditional red.shared.add into `bins + 1` slots (the extra one is a trash slot for dropped
+// samples; ptxas emits ATOMS.POPC.INC, which aggregates same-address lanes in hardware, so the post-ReLU pile-up in bin 0 is
+// not a hot spot); only non-empty bins are flushed to the caller's global histogram with red.global.add.
 #include "common.cuh"
 #include "../../include/ppq_b200.h"
 #include "variants.h"
+#include <cooperative_groups.h>
 
 namespace ppqb {
+namespace cg = cooperative_groups;
 
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
@@ -274,6 +277,35 @@ histogram_kernel(const float *__restrict__ x, int64_t n, BinParams bp, int32_t *
     hist_flush<VARIANT>(sh, bins, hist);
 }
 
+// Cluster variant (A/B: variants 7 / 8 = clusters of 2 / 4 CTAs): the CTAs of a thread-block cluster reduce their private bins through
+// distributed shared memory before touching global memory -- CTA r sums slice r of all CL private histograms with DSMEM loads and flushes
+// only that slice, so a launch issues grid / CL x bins global atomics instead of grid x bins (the flush of 148 x 4096 counters is the fixed
+// cost that separates the single-tensor collector from the multi-tensor one).
+template <class Bin, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kHistThreads)
+histogram_cluster_kernel(const float *__restrict__ x, int64_t n, BinParams bp, int32_t *__restrict__ hist) {
+    extern __shared__ int sh[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int bins = bp.bins;
+    hist_zero<0>(sh, bins);
+    Counter<0> cnt(sh, hist, bins);
+    const Bin bin(bp);
+    hist_stream<0, Bin>(x, n, (int64_t)blockIdx.x * kHistThreads + threadIdx.x, (int64_t)gridDim.x * kHistThreads, bin, cnt);
+    cluster.sync();                                                     // every CTA of the cluster has finished counting
+    const unsigned r = cluster.block_rank();
+    const int *peer[CL];
+#pragma unroll
+    for (int c = 0; c < CL; c++) peer[c] = cluster.map_shared_rank(sh, c);
+    const int slice = (bins + CL - 1) / CL, b0 = (int)r * slice, b1 = min(bins, b0 + slice);
+    for (int i = b0 + (int)threadIdx.x; i < b1; i += kHistThreads) {
+        int v = 0;
+#pragma unroll
+        for (int c = 0; c < CL; c++) v += peer[c][i];
+        if (v) atomicAdd(hist + i, v);
+    }
+    cluster.sync();                                                     // nobody exits while a peer still reads its shared memory
+}
+
 // hist_scale read from device memory (phase 2 without a host round trip)
 template <int VARIANT>
 __global__ void __launch_bounds__(kHistThreads)
@@ -373,6 +405,11 @@ static int launch_hist(const float *x, int64_t n, const BinParams &bin, int64_t 
     // 5 / 6: two 1024-thread CTAs per SM (32 registers per thread), 2 / 4 loads in flight per thread
     case 5:  histogram_kernel<0, Bin, 2, kHistThreads, 2><<<grid * 2 > sm_count() * 2 ? sm_count() * 2 : grid * 2, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     case 6:  histogram_kernel<0, Bin, 4, kHistThreads, 2><<<grid * 2 > sm_count() * 2 ? sm_count() * 2 : grid * 2, kHistThreads, smem, st>>>(x, n, bin, hist); break;
+    // 7 / 8: thread-block clusters of 2 / 4 CTAs, DSMEM pre-reduction of the private bins (grid rounded down to whole clusters)
+    case 7:  if (grid >= 2) { histogram_cluster_kernel<Bin, 2><<<grid & ~1, kHistThreads, smem, st>>>(x, n, bin, hist); break; }
+             histogram_kernel<0, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
+    case 8:  if (grid >= 4) { histogram_cluster_kernel<Bin, 4><<<grid & ~3, kHistThreads, smem, st>>>(x, n, bin, hist); break; }
+             histogram_kernel<0, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     default: histogram_kernel<0, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     }
     return (int)cudaGetLastError();

@@ -3,7 +3,7 @@
 //                     | 3 force 4 loads in flight on a persistent 148 x 8 grid
 //   "histogram":      0 default (1024-thr CTA per SM, unconditional red.shared + trash slot) | 1 generic-pointer atomicAdd
 //                     | 2 __match_any_sync aggregation | 3 global atomics like the reference | 4 the first layout (256-thr CTAs x 8 per SM)
-//                     | 5, 6 two 1024-thr CTAs per SM (32 registers), 2 / 4 loads in flight
+//                     | 5, 6 two 1024-thr CTAs per SM (32 registers), 2 / 4 loads in flight | 7, 8 clusters of 2 / 4 CTAs, DSMEM pre-reduction of the bins
 //   "linear_quant_c": 0 default (shared-memory operator table for rows shorter than 512 elements) | 1 the round-1 per-vector operator rebuild
 #pragma once
 namespace ppqb {

@@ -378,7 +378,7 @@ def test_minmax_t_and_c(ext, oracle):
         assert np.array_equal(lo.cpu().numpy(), wlo) and np.array_equal(hi.cpu().numpy(), whi), (shape, axis)
 
 
-@pytest.mark.parametrize('variant', [0, 1, 2, 3, 4])
+@pytest.mark.parametrize('variant', [0, 1, 2, 3, 4, 7, 8])
 def test_histograms_exact_vs_oracle(ext, oracle, variant):
     r = np.random.RandomState(31 + variant)
     ext.set_variant('histogram', variant)
