@@ -17,6 +17,7 @@ static int key_of(const char *name) {
     if (!strcmp(name, "histogram")) return kVarHistogram;
     if (!strcmp(name, "minmax")) return kVarMinMax;
     if (!strcmp(name, "linear_quant_c")) return kVarChannel;
+    if (!strcmp(name, "kl_search")) return kVarKlSearch;
     return -1;
 }
 }  // namespace ppqb

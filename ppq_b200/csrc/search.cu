@@ -13,6 +13,7 @@
 // log10 for the KL divergence.
 #include "common.cuh"
 #include "../../include/ppq_b200.h"
+#include "variants.h"
 
 namespace ppqb {
 
@@ -204,6 +205,121 @@ kl_search_kernel(const int32_t *__restrict__ hist_arena, int bins, const float *
     }
 }
 
+// ---- KL search, one WARP per candidate (default for bins <= 8192) ------------------------------------------------------------------------------
+// The candidates are independent given the edited histogram, its prefix sums and the memoised log10(p): the kernel above walks them one
+// after the other with four block-wide barriers each (160-196 us for 106 histograms, and the same latency for a single one -- what the
+// drop-in flow pays per rendered tensor).  Here the 32 warps of a 1024-thread CTA take one candidate each (round-robin when there are more,
+// e.g. 512 for 4-bit configs) with warp-level reductions only; the first minimum in candidate order wins, as with python's stable sort.
+// The fp64 sums associate differently from the serial kernel (lane-strided partial sums + shuffle tree), which can only matter when two
+// candidates' divergences agree to ~1e-15 relative (documented deviation 2).
+constexpr int kKlwThreads = 1024;
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kKlwThreads)
+kl_search_warp_kernel(const int32_t *__restrict__ hist_arena, int bins, const float *__restrict__ hist_scale_arena,
+                      const float *__restrict__ minmax_arena, int num_of_bits, int pow2, double min_scale, float *__restrict__ scale_out, int32_t *__restrict__ best_out) {
+    extern __shared__ unsigned char kl_smem[];
+    const int quant_bins = 1 << (num_of_bits - 1);
+    const int ncand = bins / quant_bins;                              // range(quant_bins, bins + quant_bins - 1, quant_bins), capped at bins
+    const int pre_len = max(bins + 1, kKlwThreads);
+    float *h = reinterpret_cast<float *>(kl_smem);                    // [bins]
+    double *pre = reinterpret_cast<double *>(kl_smem + (((size_t)bins * 4 + 7) & ~(size_t)7));      // [bins + 1]
+    double *logp = pre + pre_len;                                     // [bins]
+    double *loss = logp + bins;                                       // [ncand]
+    double *glogq_all = loss + ((ncand + 1) & ~1);                    // [32 warps][quant_bins]
+    float *gval_all = reinterpret_cast<float *>(glogq_all + (size_t)(kKlwThreads / 32) * quant_bins);   // [32 warps][quant_bins]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double *glogq = glogq_all + (size_t)w * quant_bins;
+    float *gval = gval_all + (size_t)w * quant_bins;
+
+    const int32_t *hist = hist_arena + (int64_t)blockIdx.x * bins;
+    const int dead = (int)((double)bins * .002);
+    for (int i = threadIdx.x; i < bins; i += kKlwThreads) {
+        float v = (float)hist[i];
+        if (i < dead) v = 0.f;
+        if (i == dead) v = 1.f;
+        h[i] = v;
+    }
+    __syncthreads();
+    {   // exclusive prefix sums (integer-valued counts: exact in fp64)
+        const int seg = (bins + kKlwThreads - 1) / kKlwThreads;
+        const int b0 = threadIdx.x * seg, b1 = min(bins, b0 + seg);
+        double s_ = 0.0;
+        for (int i = b0; i < b1; i++) s_ += (double)h[i];
+        double *tot = pre;
+        tot[threadIdx.x] = s_;
+        __syncthreads();
+        double base = 0.0;
+        for (int t = 0; t < (int)threadIdx.x; t++) base += tot[t];
+        __syncthreads();
+        double run = base;
+        for (int i = b0; i < b1; i++) { const double v = (double)h[i]; pre[i] = run; run += v; }
+        if (b1 == bins && b0 < bins) pre[bins] = run;
+        __syncthreads();
+    }
+    const float total = (float)pre[bins];
+    for (int i = threadIdx.x; i < bins; i += kKlwThreads) logp[i] = log10((double)__fdiv_rn(h[i], total) + 1e-30);
+    __syncthreads();
+
+    for (int c = w; c < ncand; c += kKlwThreads / 32) {
+        const int br = (c + 1) * quant_bins, ratio = c + 1;
+        for (int g = lane; g < quant_bins; g += 32) {
+            const int a = g * ratio;
+            int cnt = 0;
+            for (int i = a; i < a + ratio; i++) cnt += h[i] > 0.f;
+            gval[g] = __fdiv_rn((float)(pre[a + ratio] - pre[a]), (float)(cnt == 0 ? 1 : cnt));
+        }
+        __syncwarp();
+        double qs = 0.0;
+        for (int i = lane; i < br; i += 32) if (h[i] > 0.f) qs += (double)gval[i / ratio];
+        const float qsum = (float)warp_sum(qs);
+        const float tail = (float)(pre[bins] - pre[br]);
+        const float q_empty = __fdiv_rn(0.f, qsum);
+        __syncwarp();
+        for (int g = lane; g < quant_bins; g += 32) {
+            const float q = __fdiv_rn(gval[g], qsum);
+            gval[g] = q;
+            glogq[g] = log10((double)q + 1e-30);
+        }
+        __syncwarp();
+        double kl = 0.0;
+        for (int i = lane; i < br; i += 32) {
+            float pv = h[i];
+            const bool nonempty = pv > 0.f, last = (i == br - 1);
+            if (last) pv = __fadd_rn(pv, tail);
+            const float p = __fdiv_rn(pv, total);
+            const float q = nonempty ? gval[i / ratio] : q_empty;
+            if (p == 0.f && q == q) continue;
+            const double lp = last ? log10((double)p + 1e-30) : logp[i];
+            const double lq = nonempty ? glogq[i / ratio] : log10((double)q + 1e-30);
+            kl += (double)p * (lp - lq);
+        }
+        kl = warp_sum(kl);
+        if (lane == 0) loss[c] = kl;
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = -1; double best_loss = 0.0;
+        for (int c = 0; c < ncand; c++) if (best < 0 || loss[c] < best_loss) { best = c; best_loss = loss[c]; }
+        const int s_best = (best + 1) * quant_bins;
+        double hs;
+        if (minmax_arena) {
+            const double mn = (double)minmax_arena[2 * blockIdx.x], mx = (double)minmax_arena[2 * blockIdx.x + 1];
+            hs = fmax(fabs(mx), fabs(mn)) / (double)bins;
+        } else hs = (double)hist_scale_arena[blockIdx.x];
+        double scale = ((double)s_best / (double)bins) * hs * ((double)bins / (double)quant_bins);
+        scale = fmax(scale, min_scale);
+        if (pow2) scale = pow2_round(scale, true);
+        scale_out[blockIdx.x] = (float)scale;
+        if (best_out) best_out[blockIdx.x] = s_best;
+    }
+}
+
 // ---- MSE search: one CTA per histogram, one thread per candidate grid ----------------------------------------------------------
 // TorchMSEObserver.hist_to_scale_offset (range.py:456-520) drives compute_mse_loss (hist_mse.cc:3-28) over candidate (start, step)
 // grids.  The loss of a candidate is a SERIAL fp32 accumulation over the bins; each thread reproduces that order exactly, so every
@@ -308,6 +424,19 @@ int ppq_b200_kl_search(const int32_t *hist_arena, int64_t count, int64_t bins, c
     if (num_of_bits < 2 || num_of_bits > 16) return (int)cudaErrorInvalidValue;
     const int64_t qb = 1ll << (num_of_bits - 1);
     if (bins < qb || bins > 16384) return (int)cudaErrorInvalidValue;  // OBSERVER_KL_HIST_BINS_MANUL_OVERRIDE: any multiple of the quant bins works
+    if (bins <= kKlMemoBins && bins % qb == 0 && variant_of(kVarKlSearch) == 0) {        // one warp per candidate
+        const size_t ncand = (size_t)(bins / qb);
+        const size_t plen = (size_t)(bins + 1 > kKlwThreads ? bins + 1 : kKlwThreads);
+        const size_t smem_w = (((size_t)bins * 4 + 7) & ~(size_t)7) + plen * 8 + (size_t)bins * 8 + ((ncand + 1) & ~(size_t)1) * 8 +
+                              (size_t)(kKlwThreads / 32) * (size_t)qb * 12;
+        if (smem_w <= 220 * 1024) {
+            if (smem_w > 48 * 1024 && cudaFuncSetAttribute(kl_search_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+                return (int)cudaGetLastError();
+            kl_search_warp_kernel<<<(int)count, kKlwThreads, smem_w, (cudaStream_t)stream>>>(hist_arena, (int)bins, hist_scale_arena, minmax_arena,
+                                                                                               num_of_bits, power_of_2, min_scale, scale_out, best_bin_range_out);
+            return (int)cudaGetLastError();
+        }
+    }
     const size_t pre_len = (size_t)(bins + 1 > kKlThreads ? bins + 1 : kKlThreads);
     size_t smem = (((size_t)bins * 4 + 7) & ~(size_t)7) + pre_len * 8 + (((size_t)qb * 4 + 7) & ~(size_t)7);
     if (bins <= kKlMemoBins) smem += (size_t)(qb + bins) * 8;          // memoised logarithms (see the kernel)

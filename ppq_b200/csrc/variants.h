@@ -5,8 +5,9 @@
 //                     | 2 __match_any_sync aggregation | 3 global atomics like the reference | 4 the first layout (256-thr CTAs x 8 per SM)
 //                     | 5, 6 two 1024-thr CTAs per SM (32 registers), 2 / 4 loads in flight | 7, 8 clusters of 2 / 4 CTAs, DSMEM pre-reduction of the bins
 //   "linear_quant_c": 0 default (shared-memory operator table for rows shorter than 512 elements) | 1 the round-1 per-vector operator rebuild
+//   "kl_search": 0 default (one warp per candidate) | 1 the serial-candidate kernel
 #pragma once
 namespace ppqb {
-enum { kVarLinearT = 0, kVarHistogram = 1, kVarMinMax = 2, kVarChannel = 3, kVarCount = 8 };
+enum { kVarLinearT = 0, kVarHistogram = 1, kVarMinMax = 2, kVarChannel = 3, kVarKlSearch = 4, kVarCount = 8 };
 int variant_of(int key);
 }

@@ -461,9 +461,11 @@ def test_minmax_to_scale_offset_kernel_vs_reference_kats(ext):
         assert np.array_equal(o.cpu().numpy(), np.float32([r[3] for r in rows])), (sym, pow2, qmin, qmax)
 
 
-def test_kl_search_kernel_vs_reference(ext):
+@pytest.mark.parametrize('variant', [0, 1])
+def test_kl_search_kernel_vs_reference(ext, variant):
     g = load_golden('hist_search.npz')
     cs = cases_of(g)
+    ext.set_variant('kl_search', variant)            # 0: one warp per candidate (default), 1: the serial-candidate kernel
     for bits_ in (8, 4):
         sel = [c for c in cs if c['bits'] == bits_]
         hist = torch.tensor(np.stack([g[f"hist{c['k']}"] for c in sel]), dtype=torch.int32, device='cuda')
@@ -474,6 +476,38 @@ def test_kl_search_kernel_vs_reference(ext):
             want_best = round(c['scale'] / c['hist_scale'] * qb)
             assert best[i].item() == want_best, (c, best[i].item())
             assert scale[i].item() == np.float32((want_best / 4096) * float(np.float32(c['hist_scale'])) * (4096 / qb)), c
+    ext.set_variant('kl_search', 0)
+
+
+def test_kl_search_small_histograms_and_oracle_fuzz(ext, oracle):
+    """OBSERVER_KL_HIST_BINS_MANUL_OVERRIDE values below the CTA width (256, 512 bins: ADVICE r1) and random histograms of several shapes: both
+    device kernels pick the oracle's bin range (the oracle's KL search is itself pinned on the reference's, tests/test_oracle_pinning.py)."""
+    r = np.random.RandomState(91)
+    for bins, bits_ in ((256, 8), (512, 8), (1024, 8), (4096, 8), (4096, 4), (2048, 6), (8192, 8)):
+        hs_ = []
+        for kind in range(6):
+            base = r.gamma(0.6 + 0.4 * kind, 40.0, size=bins) * np.exp(-np.arange(bins) / (bins / (1.5 + kind)))
+            if kind == 4: base[bins // 3:] = 0                                  # empty tail
+            if kind == 5: base[r.rand(bins) < 0.7] = 0                          # sparse
+            hs_.append(np.floor(base).astype(np.int32))
+        hist = torch.tensor(np.stack(hs_), dtype=torch.int32, device='cuda')
+        hscale = torch.full((len(hs_),), 0.01, dtype=torch.float32, device='cuda')
+        want = [oracle.kl_search(h_, float(np.float32(0.01)), bits_, return_losses=True) for h_ in hs_]
+        for variant in (0, 1):
+            ext.set_variant('kl_search', variant)
+            try:
+                scale, best = ext.KL_Search(hist, bins, hscale, None, bits_, False, 1e-8)
+            finally:
+                ext.set_variant('kl_search', 0)
+            for i, wres in enumerate(want):
+                losses = np.asarray(wres[3], dtype=np.float64)
+                wb = wres[2]
+                got = best[i].item()
+                if got != wb:                                                   # only a numerical tie may move the argmin
+                    qb = 2 ** (bits_ - 1)
+                    assert abs(losses[got // qb - 1] - losses[wb // qb - 1]) <= 1e-12 * max(1.0, abs(losses[wb // qb - 1])), (bins, bits_, variant, i, got, wb)
+                else:
+                    assert scale[i].item() == np.float32(wres[0]), (bins, bits_, variant, i)
 
 
 def test_mse_search_kernel_vs_host_search(ext, oracle):
