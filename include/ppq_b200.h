@@ -163,10 +163,17 @@ PPQ_B200_API int ppq_b200_multi_histogram_t(const ppq_b200_tensor_desc *descs, i
  * (ppq/quantization/observer/range.py:338-349) asks for once per observed tensor and batch.  Tensor i writes
  * out[slot_i * out_stride + {0, 1}] = {sorted[clip(rn(n q))], sorted[clip(rn(n (1 - q)))]}.  `cap` = keys of a selected bucket the
  * workspace can hold per rank (bigger buckets are refined by a further streaming pass instead);
- * `workspace` is DEVICE scratch of ppq_b200_multi_quantile_workspace_bytes(count, cap) bytes. */
+ * `workspace` is DEVICE scratch of ppq_b200_multi_quantile_workspace_bytes(count, cap) bytes.
+ * `guess` (optional, DEVICE, ppq_b200_quantile_guess_words() uint32 per statistics slot, initialised once by ppq_b200_quantile_guess_init and
+ * then owned by this function) makes consecutive calls on the same slots speculative: keys beyond the thresholds remembered from the
+ * previous call are compacted during the first pass, and when they contain the requested order statistics (the usual case for consecutive
+ * calibration batches of one activation) the tensor is read ONCE.  A wrong guess only costs the regular second pass; results are always
+ * the exact order statistics. */
 PPQ_B200_API int64_t ppq_b200_multi_quantile_workspace_bytes(int count, int64_t cap);
+PPQ_B200_API int64_t ppq_b200_quantile_guess_words(void);
+PPQ_B200_API int ppq_b200_quantile_guess_init(uint32_t *guess, int64_t slots, void *stream);
 PPQ_B200_API int ppq_b200_multi_quantile_t(const ppq_b200_tensor_desc *descs, int count, int64_t max_n, float q,
-                                           float *out, int64_t out_stride, void *workspace, int64_t cap, void *stream);
+                                           float *out, int64_t out_stride, void *workspace, int64_t cap, uint32_t *guess, void *stream);
 
 /* ---- scale / offset search on the device ---------------------------------------------------------------------- */
 /* replaces minmax_to_scale_offset, ppq/quantization/observer/range.py:22-75, vectorised over `count` ranges

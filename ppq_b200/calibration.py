@@ -142,6 +142,8 @@ class ArenaCalibrator:
         self._stager = DescriptorStager(self.device, 3, rows=max(num_tensors, 16))
         self._pct: List[torch.Tensor] = []                               # per batch: [T, 2] {upper, lower} quantiles
         self._select_ws = None
+        # per-slot thresholds remembered from the previous batch: consecutive batches of one activation are selected in ONE pass over the tensor
+        self._select_guess = self.ext.Quantile_Guess_Init(num_tensors, self.minmax) if (method == 'percentile' and self.device.type == 'cuda') else None
         self.exchange_events = None                                      # set to a dict to time the exchange steps with CUDA events
         self.launches = 0
         self.reset()
@@ -181,7 +183,7 @@ class ArenaCalibrator:
             need = self.ext.Multi_Quantile_Workspace_Bytes(len(tensors), self.select_cap)
             if self._select_ws is None or self._select_ws.numel() < need:
                 self._select_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self.ext.Multi_Quantile_T(descs, max_n, self.percentile, self._batch_quantiles(), 2, self._select_ws, self.select_cap)
+            self.ext.Multi_Quantile_T(descs, max_n, self.percentile, self._batch_quantiles(), 2, self._select_ws, self.select_cap, self._select_guess)
             self.launches += 8
             return
         if self.phase == 1:

@@ -49,7 +49,15 @@ struct SelectState {                           // one per tensor, in the caller'
     unsigned int kmin[2], kmax[2];             // min / max key seen in the bucket during a refining pass
     long long rank[2];                         // remaining rank inside the current bucket
     long long count[2];                        // population of the current bucket
+    // speculation (table form with a `guess` buffer): candidates beyond last call's thresholds are compacted during pass 0
+    unsigned int spec;                         // 1: this call speculates
+    unsigned int g[2], k[2], d[2];             // thresholds {hi: key >= g[0], lo: key <= g[1]}, last call's selected keys, threshold margins
+    unsigned int eqc[2];                       // candidates equal to k[r] (counted, not stored: post-ReLU tensors select an exact 0 among millions)
+    unsigned int veq[2], vkey[2];              // for the finish: `veq` virtual copies of `vkey` belong to the compacted multiset of rank r
+    unsigned int pad2_;
 };
+constexpr int kGuessWords = 8;                 // per slot: {g_hi, k_hi, d_hi, 0, g_lo, k_lo, d_lo, 0}
+constexpr unsigned kSpecMarginInit = 1u << 19, kSpecMarginMin = 1u << 12, kSpecMarginMax = 1u << 24;
 
 __host__ __device__ constexpr int level_shift(int level) { return level == 0 ? 21 : (level == 1 ? 10 : 0); }
 __host__ __device__ constexpr uint32_t level_dmask(int level) { return level == 2 ? 0x3FFu : 0x7FFu; }
@@ -76,7 +84,7 @@ __device__ __forceinline__ long long quantile_rank(int64_t n, float frac) {
 
 // one CTA per tensor.  q_mode: ranks = {rn(n q), rn(n (1 - q))};  otherwise explicit ranks (isotone)
 __global__ void select_init_kernel(SelectState *states, const ppq_b200_tensor_desc *descs, int64_t n_single, float q, int q_mode,
-                                   long long r0, long long r1) {
+                                   long long r0, long long r1, const uint32_t *__restrict__ guess = nullptr) {
     SelectState *st = states + blockIdx.x;
     for (int i = threadIdx.x; i < 2 * kDigits; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
     if (threadIdx.x == 0) {
@@ -86,6 +94,11 @@ __global__ void select_init_kernel(SelectState *states, const ppq_b200_tensor_de
         st->ccount[0] = st->ccount[1] = 0u; st->cbuf[0] = 0u; st->cbuf[1] = 1u; st->clevel[0] = st->clevel[1] = 0u;
         st->compacted[0] = st->compacted[1] = 0u; st->kmin[0] = st->kmin[1] = 0xFFFFFFFFu; st->kmax[0] = st->kmax[1] = 0u;
         st->rank[0] = r0; st->rank[1] = r1; st->count[0] = st->count[1] = n;
+        st->spec = guess ? 1u : 0u; st->eqc[0] = st->eqc[1] = 0u; st->veq[0] = st->veq[1] = 0u; st->vkey[0] = st->vkey[1] = 0u;
+        if (guess) {
+            const uint32_t *gw = guess + (int64_t)descs[blockIdx.x].slot * kGuessWords;
+            st->g[0] = gw[0]; st->k[0] = gw[1]; st->d[0] = gw[2]; st->g[1] = gw[4]; st->k[1] = gw[5]; st->d[1] = gw[6];
+        } else { st->g[0] = st->k[0] = 0xFFFFFFFFu; st->g[1] = st->k[1] = 0u; st->d[0] = st->d[1] = kSpecMarginInit; }
     }
 }
 
@@ -122,6 +135,32 @@ __device__ __noinline__ void select_scan(SelectState *st, long long cap) {
     __shared__ unsigned long long s_before, s_cnt;
     const int t = threadIdx.x;
     const bool shared_in = st->shared != 0;
+    if (LEVEL == 0 && st->spec) {
+        // Did the candidates compacted during pass 0 (keys beyond last call's thresholds; copies of last call's key only counted) contain
+        // the requested order statistic?  hi: the n - r0 largest elements must all be candidates; lo: the r1 + 1 smallest ones.
+        __syncthreads();
+        if (t == 0) {
+            const long long n = st->count[0];
+            for (int r = 0; r < 2; r++) {
+                const long long app = (long long)__ldcg(&st->ccount[r]), eq = (long long)__ldcg(&st->eqc[r]), cnt = app + eq;
+                const long long need = r == 0 ? n - st->rank[0] : st->rank[1] + 1;
+                unsigned int d = st->d[r];
+                if (app <= cap && cnt >= need) {
+                    st->mode[r] = kModeCompact; st->compacted[r] = 1u; st->clevel[r] = 0u; st->prefix[r] = 0u; st->cbuf[r] = (unsigned)r;
+                    st->rank[r] = r == 0 ? cnt - need : st->rank[1];
+                    st->veq[r] = (unsigned)eq; st->vkey[r] = st->k[r];
+                    if (cnt > 4 * need + 64 && d > kSpecMarginMin) d >>= 1;          // far more candidates than needed: tighten the threshold
+                } else {
+                    st->ccount[r] = 0u;                                              // the buffer goes back to the regular compaction of pass 1
+                    const bool first_call = r == 0 ? st->g[0] == 0xFFFFFFFFu : st->g[1] == 0u;   // nothing was guessed yet: no verdict on the margin
+                    if (app > cap) { if (d > kSpecMarginMin) d >>= 1; }
+                    else if (!first_call && d < kSpecMarginMax) d <<= 1;             // too few candidates: the distribution moved, widen
+                }
+                st->d[r] = d;
+            }
+        }
+        __syncthreads();
+    }
     for (int r = 0; r < 2; r++) {
         const int src = (r == 1 && shared_in) ? 0 : r;
         const unsigned int mode = st->mode[r];                          // uniform
@@ -147,7 +186,8 @@ __device__ __noinline__ void select_scan(SelectState *st, long long cap) {
     }
     for (int i = t; i < 2 * kDigits; i += TPB) (&st->hist[0][0])[i] = 0ull;
     if (t == 0) {
-        const bool same = st->prefix[0] == st->prefix[1] && st->mode[0] == st->mode[1] && st->mode[0] != kModeDone;
+        const bool same = st->prefix[0] == st->prefix[1] && st->mode[0] == st->mode[1] && st->mode[0] != kModeDone &&
+                          !st->compacted[0] && !st->compacted[1];
         st->shared = same ? 1u : 0u;
         if (st->mode[0] == kModeCompact && !st->compacted[0]) st->cbuf[0] = 0u;
         if (st->mode[1] == kModeCompact && !st->compacted[1]) st->cbuf[1] = same ? 0u : 1u;
@@ -263,6 +303,82 @@ __device__ __forceinline__ bool select_pass(const float *__restrict__ x, int64_t
     return true;
 }
 
+// Pass 0 with speculation (table form, `guess` given): the digit histogram of every element as in select_pass<0>, and on the way every key
+// beyond the thresholds remembered from the previous call of this slot (the previous batch of the same activation: the tail moves little
+// from batch to batch) is compacted -- except copies of the previously selected key, which are only counted.  When the candidates turn out
+// to contain the requested order statistics (select_scan<0>), the finish selects among them and the tensor has been read ONCE.
+template <int TPB>
+__device__ __forceinline__ void select_pass0_spec(const float *__restrict__ x, int64_t a, int64_t b, int64_t first, int64_t stride,
+                                                  SelectState *__restrict__ st, uint32_t *__restrict__ bufs, int64_t cap, int (*sh)[kDigits], unsigned int *sh_cnt) {
+    constexpr int kHalf = kStage / 2;                                     // sh[1] holds both staging lists: hi candidates, then lo candidates
+    const uint32_t g_hi = st->g[0], k_hi = st->k[0], g_lo = st->g[1], k_lo = st->k[1];
+    for (int i = threadIdx.x; i < 2 * kDigits; i += TPB) (&sh[0][0])[i] = 0;
+    if (threadIdx.x < 2) sh_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(&sh[0][0]);
+    uint32_t *buf[2] = {bufs, bufs + cap};
+    unsigned eq_hi = 0, eq_lo = 0;
+    auto append = [&](int r, uint32_t k) {
+        const unsigned idx = atomicAdd(&sh_cnt[r], 1u);
+        if (idx < (unsigned)kHalf) sh[1][r * kHalf + idx] = (int)k;
+        else { const unsigned gi = atomicAdd(&st->ccount[r], 1u); if ((long long)gi < cap) buf[r][gi] = k; }
+    };
+    auto candidate = [&](uint32_t k) {
+        if (k >= g_hi) { if (k == k_hi) eq_hi++; else append(0, k); }
+        if (k <= g_lo) { if (k == k_lo) eq_lo++; else append(1, k); }
+    };
+    auto digit = [&](uint32_t k) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + (k >> 21) * 4u) : "memory"); };
+    auto visit4 = [&](const float4 &v) {
+        const uint32_t k0 = order_key(v.x), k1 = order_key(v.y), k2 = order_key(v.z), k3 = order_key(v.w);
+        digit(k0); digit(k1); digit(k2); digit(k3);
+        if (max(max(k0, k1), max(k2, k3)) >= g_hi || min(min(k0, k1), min(k2, k3)) <= g_lo) { candidate(k0); candidate(k1); candidate(k2); candidate(k3); }
+    };
+    auto visit1 = [&](float f) { const uint32_t k = order_key(f); digit(k); candidate(k); };
+    stream_range<4, false>(x, a, b, first, stride, visit4, visit1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kDigits; i += TPB) if (sh[0][i]) atomicAdd(&st->hist[0][i], (unsigned long long)sh[0][i]);
+    eq_hi = __reduce_add_sync(0xffffffffu, eq_hi); eq_lo = __reduce_add_sync(0xffffffffu, eq_lo);
+    if ((threadIdx.x & 31) == 0) { if (eq_hi) atomicAdd(&st->eqc[0], eq_hi); if (eq_lo) atomicAdd(&st->eqc[1], eq_lo); }
+    __shared__ unsigned int s_base0[2];
+    for (int r = 0; r < 2; r++) {
+        const unsigned m = min(sh_cnt[r], (unsigned)kHalf);
+        if (threadIdx.x == 0 && m) s_base0[r] = atomicAdd(&st->ccount[r], m);
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < m; i += TPB) if ((long long)(s_base0[r] + i) < cap) buf[r][s_base0[r] + i] = (uint32_t)sh[1][r * kHalf + i];
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+multi_select_pass0_spec_kernel(const ppq_b200_tensor_desc *__restrict__ descs, int count, SelectState *__restrict__ states,
+                               uint32_t *__restrict__ bufs, int64_t cap) {
+    __shared__ int sh[2][kDigits];
+    __shared__ unsigned int sh_cnt[2];
+    extern __shared__ long long prefix[];                              // [count + 1]
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        for (int t = 0; t < count; t++) { prefix[t] = run; run += descs[t].n; }
+        prefix[count] = run;
+    }
+    __syncthreads();
+    const int64_t total = prefix[count];
+    int64_t span = (total + gridDim.x - 1) / gridDim.x;
+    span = (span + 3) & ~(int64_t)3;
+    const int64_t s0 = (int64_t)blockIdx.x * span, s1 = (s0 + span) < total ? (s0 + span) : total;
+    if (s0 >= total) return;
+    int t = 0;
+    { int lo = 0, hi = count - 1; while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (prefix[mid] <= s0) lo = mid; else hi = mid - 1; } t = lo; }
+    for (; t < count && prefix[t] < s1; t++) {
+        const ppq_b200_tensor_desc d = descs[t];
+        int64_t a = s0 - prefix[t]; if (a < 0) a = 0;
+        int64_t b = s1 - prefix[t]; if (b > d.n) b = d.n;
+        a = (a + 3) & ~(int64_t)3; if (a > d.n) a = d.n;
+        if (b < d.n) b = (b + 3) & ~(int64_t)3; if (b > d.n) b = d.n;
+        if (b <= a) continue;
+        select_pass0_spec<kSelThreads>(d.x, a, b, threadIdx.x, kSelThreads, states + t, bufs + (int64_t)t * 2 * cap, cap, sh, sh_cnt);
+        __syncthreads();
+    }
+}
+
 // ---- single tensor: the whole grid interleaves over the tensor, the last CTA to finish resolves the pass ------------------------------
 template <int LEVEL, int TPB>
 __global__ void __launch_bounds__(TPB, LEVEL == 0 ? 2 : 6)
@@ -331,7 +447,7 @@ select_scan_kernel(SelectState *states, int64_t cap) {
 // ---- finish: one CTA per (tensor, rank) selects among the compacted keys (or just reports a resolved key) -------------------------------
 __global__ void __launch_bounds__(kSelThreads)
 select_finish_kernel(const SelectState *__restrict__ states, const uint32_t *__restrict__ bufs, int64_t cap,
-                     const ppq_b200_tensor_desc *__restrict__ descs, float *__restrict__ out, int64_t out_stride) {
+                     const ppq_b200_tensor_desc *__restrict__ descs, float *__restrict__ out, int64_t out_stride, uint32_t *__restrict__ guess = nullptr) {
     __shared__ int sh[kDigits];
     __shared__ unsigned int s_digit;
     __shared__ unsigned long long s_before, s_cnt;
@@ -352,6 +468,8 @@ select_finish_kernel(const SelectState *__restrict__ states, const uint32_t *__r
                 const uint32_t v = __ldcg(keys + i);
                 if ((v & pmask) == (key & pmask)) atomicAdd(&sh[(v >> shift) & dmask], 1);
             }
+            if (threadIdx.x == 0 && st->veq[r] && (st->vkey[r] & pmask) == (key & pmask))      // the counted-only copies of last call's key
+                atomicAdd(&sh[(st->vkey[r] >> shift) & dmask], (int)st->veq[r]);
             __syncthreads();
             block_pick<kSelThreads>([&](int i) { return (unsigned long long)sh[i]; }, k, &s_digit, &s_before, &s_cnt);
             key |= s_digit << shift;
@@ -359,7 +477,15 @@ select_finish_kernel(const SelectState *__restrict__ states, const uint32_t *__r
             __syncthreads();
         }
     }
-    if (threadIdx.x == 0) *dst = key_to_float(key);
+    if (threadIdx.x == 0) {
+        *dst = key_to_float(key);
+        if (guess) {                                                    // thresholds for the next call of this slot: the selected key -/+ the margin
+            uint32_t *gw = guess + (int64_t)descs[tensor].slot * kGuessWords + 4 * r;
+            const uint32_t d = st->d[r];
+            gw[0] = r == 0 ? (key > d ? key - d : 0u) : (key < 0xFFFFFFFFu - d ? key + d : 0xFFFFFFFFu);
+            gw[1] = key; gw[2] = d; gw[3] = 0u;
+        }
+    }
 }
 
 static inline int grid_pass0(int64_t n) {
@@ -393,6 +519,17 @@ extern "C" {
 
 int64_t ppq_b200_quantile_workspace_bytes(void) { return (int64_t)sizeof(SelectState) + 2 * kDefaultCap * (int64_t)sizeof(uint32_t); }
 
+int64_t ppq_b200_quantile_guess_words(void) { return kGuessWords; }
+
+int ppq_b200_quantile_guess_init(uint32_t *guess, int64_t slots, void *stream) {
+    if (!guess || slots <= 0) return (int)cudaErrorInvalidValue;
+    // thresholds that select nothing (key >= 0xFFFFFFFF / key <= 0), so that the first call takes the regular two-pass route
+    static const uint32_t row[kGuessWords] = {0xFFFFFFFFu, 0xFFFFFFFFu, kSpecMarginInit, 0u, 0u, 0u, kSpecMarginInit, 0u};
+    for (int64_t i = 0; i < slots; i++)
+        if (cudaMemcpyAsync(guess + i * kGuessWords, row, sizeof(row), cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess) return (int)cudaGetLastError();
+    return 0;
+}
+
 int64_t ppq_b200_multi_quantile_workspace_bytes(int count, int64_t cap) {
     if (count <= 0 || cap <= 0) return 0;
     return (int64_t)count * ((int64_t)sizeof(SelectState) + 2 * cap * (int64_t)sizeof(uint32_t));
@@ -404,7 +541,7 @@ int ppq_b200_quantile_t(const float *x, int64_t n, float q, float *out2, void *w
 }
 
 int ppq_b200_multi_quantile_t(const ppq_b200_tensor_desc *descs, int count, int64_t max_n, float q, float *out, int64_t out_stride,
-                              void *workspace, int64_t cap, void *stream) {
+                              void *workspace, int64_t cap, uint32_t *guess, void *stream) {
     if (count <= 0 || max_n <= 0 || !descs || !out || !workspace || cap <= 0 || out_stride < 2) return (int)cudaErrorInvalidValue;
     const size_t smem = (size_t)(count + 1) * sizeof(long long);
     if (smem > 24 * 1024) return (int)cudaErrorInvalidValue;
@@ -413,14 +550,17 @@ int ppq_b200_multi_quantile_t(const ppq_b200_tensor_desc *descs, int count, int6
     uint32_t *bufs = (uint32_t *)(states + count);
     int64_t work = (int64_t)count * max_n;
     int g0 = grid_pass0(work), g1 = grid_filter(work);
-    select_init_kernel<<<count, 1024, 0, s>>>(states, descs, 0, q, 1, 0, 0);
-    multi_select_pass_kernel<0, kSelThreads><<<g0, kSelThreads, smem, s>>>(descs, count, states, bufs, cap);
+    select_init_kernel<<<count, 1024, 0, s>>>(states, descs, 0, q, 1, 0, 0, guess);
+    if (guess) {                                                        // 64 registers per thread: one 1024-thread CTA per SM
+        const int gs = g0 > sm_count() ? sm_count() : g0;
+        multi_select_pass0_spec_kernel<<<gs, kSelThreads, smem, s>>>(descs, count, states, bufs, cap);
+    } else multi_select_pass_kernel<0, kSelThreads><<<g0, kSelThreads, smem, s>>>(descs, count, states, bufs, cap);
     select_scan_kernel<0><<<count, kSelThreads, 0, s>>>(states, cap);
     multi_select_pass_kernel<1, kFilterThreads><<<g1, kFilterThreads, smem, s>>>(descs, count, states, bufs, cap);
     select_scan_kernel<1><<<count, kSelThreads, 0, s>>>(states, cap);
     multi_select_pass_kernel<2, kFilterThreads><<<g1, kFilterThreads, smem, s>>>(descs, count, states, bufs, cap);
     select_scan_kernel<2><<<count, kSelThreads, 0, s>>>(states, cap);
-    select_finish_kernel<<<2 * count, kSelThreads, 0, s>>>(states, bufs, cap, descs, out, out_stride);
+    select_finish_kernel<<<2 * count, kSelThreads, 0, s>>>(states, bufs, cap, descs, out, out_stride, guess);
     return (int)cudaGetLastError();
 }
 

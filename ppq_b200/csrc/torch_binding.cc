@@ -230,8 +230,9 @@ void Multi_Histogram_T(const Tensor &descs, const int64_t max_numel, const Tenso
                 "Multi_Histogram_T");
 }
 // out: float tensor, tensor i writes out.flat[slot_i * out_stride + {0, 1}] = {upper, lower} quantile; workspace: uint8 scratch
+// guess: optional int32 tensor [slots, Quantile_Guess_Words()] made by Quantile_Guess_Init -- consecutive calls on the same slots become one-pass
 void Multi_Quantile_T(const Tensor &descs, const int64_t max_numel, const float q, Tensor &out, const int64_t out_stride, Tensor &workspace,
-                      const int64_t cap) {
+                      const int64_t cap, const c10::optional<Tensor> &guess) {
     CheckTensor(descs, at::kLong, "Descriptors(Expect to be INT64)");
     CheckTensor(out, at::kFloat, "Quantiles(Expect to be FP32)");
     if (descs.dim() != 2 || descs.size(1) != 3 || !descs.is_contiguous()) throw KernelFailure("Kernel Failure, descriptor table must be [count, 3] int64.");
@@ -239,8 +240,20 @@ void Multi_Quantile_T(const Tensor &descs, const int64_t max_numel, const float 
     if (workspace.scalar_type() != at::kByte || workspace.numel() < ppq_b200_multi_quantile_workspace_bytes(count, cap))
         throw KernelFailure("Kernel Failure, quantile workspace is too small (see Multi_Quantile_Workspace_Bytes).");
     const c10::cuda::CUDAGuard guard(descs.device());
+    uint32_t *gp = nullptr;
+    if (guess.has_value()) {
+        CheckTensor(*guess, at::kInt, "Guess(Expect to be INT32)");
+        if (!guess->is_contiguous() || guess->numel() % ppq_b200_quantile_guess_words() != 0) throw KernelFailure("Kernel Failure, quantile guess buffer has a wrong shape.");
+        gp = reinterpret_cast<uint32_t *>(guess->data_ptr<int>());
+    }
     CheckStatus(ppq_b200_multi_quantile_t(reinterpret_cast<const ppq_b200_tensor_desc *>(descs.data_ptr<int64_t>()), count, max_numel, q,
-                                          out.data_ptr<float>(), out_stride, workspace.data_ptr(), cap, Stream()), "Multi_Quantile_T");
+                                          out.data_ptr<float>(), out_stride, workspace.data_ptr(), cap, gp, Stream()), "Multi_Quantile_T");
+}
+Tensor Quantile_Guess_Init(const int64_t slots, const Tensor &like) {
+    const c10::cuda::CUDAGuard guard(like.device());
+    Tensor g = at::empty({slots, ppq_b200_quantile_guess_words()}, like.options().dtype(at::kInt));
+    CheckStatus(ppq_b200_quantile_guess_init(reinterpret_cast<uint32_t *>(g.data_ptr<int>()), slots, Stream()), "Quantile_Guess_Init");
+    return g;
 }
 int64_t Multi_Quantile_Workspace_Bytes(const int count, const int64_t cap) { return ppq_b200_multi_quantile_workspace_bytes(count, cap); }
 std::vector<Tensor> MinMax_To_Scale_Offset(const Tensor &mins, const Tensor &maxs, const int64_t stride, const int quant_min,
@@ -335,6 +348,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("Multi_MinMax_T", Multi_MinMax_T, "Multi_MinMax_T");
     m.def("Multi_Histogram_T", Multi_Histogram_T, "Multi_Histogram_T");
     m.def("Multi_Quantile_T", Multi_Quantile_T, "Multi_Quantile_T");
+    m.def("Quantile_Guess_Init", Quantile_Guess_Init, "Quantile_Guess_Init");
     m.def("Multi_Quantile_Workspace_Bytes", Multi_Quantile_Workspace_Bytes, "Multi_Quantile_Workspace_Bytes");
     m.def("MinMax_To_Scale_Offset", MinMax_To_Scale_Offset, "MinMax_To_Scale_Offset");
     m.def("Hist_Scale_From_MinMax", Hist_Scale_From_MinMax, "Hist_Scale_From_MinMax");

@@ -95,11 +95,49 @@ def test_multi_tensor_quantile_matches_single_launches(ext):
         for cap in (1 << 16, 64):
             ws = torch.empty(ext.Multi_Quantile_Workspace_Bytes(len(xs), cap), dtype=torch.uint8, device='cuda')
             out = torch.full((len(xs), 3), -7.0, device='cuda')                  # out_stride 3: the third column must stay untouched
-            ext.Multi_Quantile_T(descs, max(sizes), q, out, 3, ws, cap)
+            ext.Multi_Quantile_T(descs, max(sizes), q, out, 3, ws, cap, None)
             assert torch.equal(out[slots, :2], want), (q, cap, out, want)
             assert bool((out[:, 2] == -7.0).all())
     with pytest.raises(RuntimeError, match='workspace is too small'):
-        ext.Multi_Quantile_T(descs, max(sizes), 0.5, torch.zeros(len(xs), 2, device='cuda'), 2, torch.empty(16, dtype=torch.uint8, device='cuda'), 64)
+        ext.Multi_Quantile_T(descs, max(sizes), 0.5, torch.zeros(len(xs), 2, device='cuda'), 2, torch.empty(16, dtype=torch.uint8, device='cuda'), 64, None)
+
+
+def test_speculative_quantile_over_consecutive_batches(ext):
+    """With a `guess` buffer the select compacts, during its first pass, the keys beyond the thresholds remembered from the previous call of the
+    same slot -- consecutive calibration batches of one activation then need ONE pass over the tensor.  Whatever the guess is worth (first call,
+    a distribution that drifts, jumps, collapses to a constant, a tiny workspace that overflows), the results must be the exact order statistics."""
+    g = torch.Generator(device='cuda').manual_seed(9)
+    sizes = [401408, 150528, 5, 1 << 20, 25088, 3000]
+    slots = [2, 0, 5, 1, 4, 3]
+    q = 0.9999
+
+    def batch(step):
+        xs = []
+        for i, n in enumerate(sizes):
+            scale = (1 + i) * (1.0 + 0.02 * step)                                # slow drift
+            if step == 6: scale *= 3.0                                          # jump up: too few candidates -> regular second pass
+            if step == 8: scale *= 0.2                                          # jump down: too many candidates
+            x = torch.randn(n, device='cuda', generator=g) * scale
+            if i % 2 == 1: x = torch.relu(x)                                    # lower quantile = an exact 0 among ~n/2 zeros
+            if step == 10 and i == 0: x = torch.full((n,), 2.5, device='cuda')  # constant tensor
+            if step == 11 and i == 3: x = torch.randint(-2, 3, (n,), device='cuda', generator=g).float()
+            xs.append(x)
+        return xs
+
+    for cap in (1 << 16, 256):
+        guess = ext.Quantile_Guess_Init(len(sizes), torch.zeros(1, device='cuda'))
+        ws = torch.empty(ext.Multi_Quantile_Workspace_Bytes(len(sizes), cap), dtype=torch.uint8, device='cuda')
+        for step in range(13):
+            xs = batch(step)
+            descs = torch.tensor([[x.data_ptr(), x.numel(), s] for x, s in zip(xs, slots)], dtype=torch.int64, device='cuda')
+            out = torch.zeros(len(sizes), 2, device='cuda')
+            ext.Multi_Quantile_T(descs, max(sizes), q, out, 2, ws, cap, guess)
+            for x, s in zip(xs, slots):
+                srt = torch.sort(x)[0]; n = x.numel()
+                ia = int(min(max(np.rint(np.float32(n) * np.float32(q)), 0), n - 1)); ib = int(min(max(np.rint(np.float32(n) * (np.float32(1) - np.float32(q))), 0), n - 1))
+                assert torch.equal(out[s], torch.stack([srt[ia], srt[ib]])), (cap, step, n, out[s], srt[ia], srt[ib])
+        gk = guess.view(len(sizes), 2, 4)
+        assert bool((gk[:, :, 3] == 0).all())                                   # layout: {threshold, last key, margin, 0} per side
 
 
 def test_isotone_top2_bottom2(ext, ref):

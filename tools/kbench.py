@@ -93,7 +93,9 @@ def main():
         cap = 1 << 16
         ws = torch.empty(ext.Multi_Quantile_Workspace_Bytes(16, cap), dtype=torch.uint8, device=dev)
         out = torch.zeros(16, 2, device=dev)
-        report('multi_quantile_t 16 tensors of n/16 (one table)', timeit(lambda i: ext.Multi_Quantile_T(descs[i], n // 16, 0.9999, out, 2, ws, cap), args.reps, nbuf), 4)
+        report('multi_quantile_t 16 tensors of n/16 (one table)', timeit(lambda i: ext.Multi_Quantile_T(descs[i], n // 16, 0.9999, out, 2, ws, cap, None), args.reps, nbuf), 4)
+        guess = ext.Quantile_Guess_Init(16, out)
+        report('  same, speculative (thresholds from the previous call)', timeit(lambda i: ext.Multi_Quantile_T(descs[i], n // 16, 0.9999, out, 2, ws, cap, guess), args.reps, nbuf), 4)
     if 'lc' in only:
         for shape, axis in (((n // 4608, 4608), 0), ((n // 512, 512), 0), ((n // 64, 64), 0), ((8, n // 8 // 3136, 3136), 1), ((n // 9, 9), 0), ((n // 768, 768), 1)):
             C = shape[axis]
