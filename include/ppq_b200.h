@@ -140,6 +140,9 @@ PPQ_B200_API int ppq_b200_histogram_t_dscale(const float *x, int64_t n, const fl
  * `workspace` is DEVICE scratch of ppq_b200_quantile_workspace_bytes() bytes. */
 PPQ_B200_API int64_t ppq_b200_quantile_workspace_bytes(void);
 PPQ_B200_API int ppq_b200_quantile_t(const float *x, int64_t n, float q, float *out2, void *workspace, void *stream);
+/* the same with a one-slot `guess` buffer (see ppq_b200_multi_quantile_t): consecutive calls on batches of one activation -- what
+ * TorchPercentileObserver.observe does (range.py:338-349) -- read the tensor once when the previous call's thresholds still hold. */
+PPQ_B200_API int ppq_b200_quantile_t_guess(const float *x, int64_t n, float q, float *out2, void *workspace, uint32_t *guess, void *stream);
 /* replaces Isotone_T, sort.cu:23-40, 61-73: out4 = {sorted[n-1], sorted[n-2], sorted[0], sorted[1]} (same workspace). */
 PPQ_B200_API int ppq_b200_isotone_t(const float *x, int64_t n, float *out4, void *workspace, void *stream);
 

@@ -96,7 +96,7 @@ __global__ void select_init_kernel(SelectState *states, const ppq_b200_tensor_de
         st->rank[0] = r0; st->rank[1] = r1; st->count[0] = st->count[1] = n;
         st->spec = guess ? 1u : 0u; st->eqc[0] = st->eqc[1] = 0u; st->veq[0] = st->veq[1] = 0u; st->vkey[0] = st->vkey[1] = 0u;
         if (guess) {
-            const uint32_t *gw = guess + (int64_t)descs[blockIdx.x].slot * kGuessWords;
+            const uint32_t *gw = guess + (descs ? (int64_t)descs[blockIdx.x].slot : 0) * kGuessWords;
             st->g[0] = gw[0]; st->k[0] = gw[1]; st->d[0] = gw[2]; st->g[1] = gw[4]; st->k[1] = gw[5]; st->d[1] = gw[6];
         } else { st->g[0] = st->k[0] = 0xFFFFFFFFu; st->g[1] = st->k[1] = 0u; st->d[0] = st->d[1] = kSpecMarginInit; }
     }
@@ -349,6 +349,22 @@ __device__ __forceinline__ void select_pass0_spec(const float *__restrict__ x, i
 }
 
 __global__ void __launch_bounds__(kSelThreads, 1)
+select_pass0_spec_kernel(const float *__restrict__ x, int64_t n, SelectState *__restrict__ st, uint32_t *__restrict__ bufs, int64_t cap) {
+    __shared__ int sh[2][kDigits];
+    __shared__ unsigned int sh_cnt[2];
+    __shared__ bool is_last;
+    select_pass0_spec<kSelThreads>(x, 0, n, (int64_t)blockIdx.x * kSelThreads + threadIdx.x, (int64_t)gridDim.x * kSelThreads, st, bufs, cap, sh, sh_cnt);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->done, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        select_scan<0, kSelThreads>(st, cap);
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1)
 multi_select_pass0_spec_kernel(const ppq_b200_tensor_desc *__restrict__ descs, int count, SelectState *__restrict__ states,
                                uint32_t *__restrict__ bufs, int64_t cap) {
     __shared__ int sh[2][kDigits];
@@ -480,7 +496,7 @@ select_finish_kernel(const SelectState *__restrict__ states, const uint32_t *__r
     if (threadIdx.x == 0) {
         *dst = key_to_float(key);
         if (guess) {                                                    // thresholds for the next call of this slot: the selected key -/+ the margin
-            uint32_t *gw = guess + (int64_t)descs[tensor].slot * kGuessWords + 4 * r;
+            uint32_t *gw = guess + (descs ? (int64_t)descs[tensor].slot : 0) * kGuessWords + 4 * r;
             const uint32_t d = st->d[r];
             gw[0] = r == 0 ? (key > d ? key - d : 0u) : (key < 0xFFFFFFFFu - d ? key + d : 0xFFFFFFFFu);
             gw[1] = key; gw[2] = d; gw[3] = 0u;
@@ -499,15 +515,19 @@ static inline int grid_filter(int64_t n) {
     return (int)(g < 1 ? 1 : g);
 }
 
-static int select_two(const float *x, int64_t n, int q_mode, float q, long long r0, long long r1, float *out, void *workspace, cudaStream_t s) {
+static int select_two(const float *x, int64_t n, int q_mode, float q, long long r0, long long r1, float *out, void *workspace, cudaStream_t s,
+                      uint32_t *guess = nullptr) {
     SelectState *st = (SelectState *)workspace;
     uint32_t *bufs = (uint32_t *)(st + 1);
     const int64_t cap = kDefaultCap;
-    select_init_kernel<<<1, 1024, 0, s>>>(st, nullptr, n, q, q_mode, r0, r1);
-    select_pass_kernel<0, kSelThreads><<<grid_pass0(n), kSelThreads, 0, s>>>(x, n, st, bufs, cap);
+    select_init_kernel<<<1, 1024, 0, s>>>(st, nullptr, n, q, q_mode, r0, r1, guess);
+    if (guess) {
+        const int g0 = grid_pass0(n);
+        select_pass0_spec_kernel<<<g0 > sm_count() ? sm_count() : g0, kSelThreads, 0, s>>>(x, n, st, bufs, cap);
+    } else select_pass_kernel<0, kSelThreads><<<grid_pass0(n), kSelThreads, 0, s>>>(x, n, st, bufs, cap);
     select_pass_kernel<1, kFilterThreads><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
     select_pass_kernel<2, kFilterThreads><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
-    select_finish_kernel<<<2, kSelThreads, 0, s>>>(st, bufs, cap, nullptr, out, 0);
+    select_finish_kernel<<<2, kSelThreads, 0, s>>>(st, bufs, cap, nullptr, out, 0, guess);
     return (int)cudaGetLastError();
 }
 
@@ -538,6 +558,11 @@ int64_t ppq_b200_multi_quantile_workspace_bytes(int count, int64_t cap) {
 int ppq_b200_quantile_t(const float *x, int64_t n, float q, float *out2, void *workspace, void *stream) {
     if (n <= 0 || !x || !out2 || !workspace) return (int)cudaErrorInvalidValue;
     return select_two(x, n, 1, q, 0, 0, out2, workspace, (cudaStream_t)stream);
+}
+
+int ppq_b200_quantile_t_guess(const float *x, int64_t n, float q, float *out2, void *workspace, uint32_t *guess, void *stream) {
+    if (n <= 0 || !x || !out2 || !workspace) return (int)cudaErrorInvalidValue;
+    return select_two(x, n, 1, q, 0, 0, out2, workspace, (cudaStream_t)stream, guess);
 }
 
 int ppq_b200_multi_quantile_t(const ppq_b200_tensor_desc *descs, int count, int64_t max_n, float q, float *out, int64_t out_stride,

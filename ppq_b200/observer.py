@@ -235,13 +235,18 @@ class TorchPercentileObserver(BaseTensorObserver):
         super().__init__(watch_on, quant_cfg)
         self._percentile = quant_cfg.detail.get(OBSERVER_PERCENTILE_MANUL_OVERRIDE, OBSERVER_PERCENTILE)
         self._percentile_collector = []
+        self._guess = None                      # thresholds remembered from the previous batch: the select reads a batch once when they still hold
 
     @torch.no_grad()
     def observe(self, value: torch.Tensor):
         if not state_is(self._quant_cfg, 'INITIAL'): return
         assert value is not None and value.numel() > 0, 'You are observing an empty tensor.'
         if self._quant_cfg.policy.has_property(QuantizationProperty.PER_TENSOR):
-            self._percentile_collector.append(CUDA.Quantile(value, self._percentile).view(1, -1))
+            if not value.is_cuda:
+                self._percentile_collector.append(CUDA.Quantile(value, self._percentile).view(1, -1))       # raises: there is no CPU path here
+            else:
+                if self._guess is None or self._guess.device != value.device: self._guess = _ext().Quantile_Guess_Init(1, value)
+                self._percentile_collector.append(_ext().Quantile_T_Guess(value, self._percentile, self._guess).view(1, -1))
         elif self._quant_cfg.policy.has_property(QuantizationProperty.PER_CHANNEL):
             raise PermissionError('Percentile observer can not deal with per channel quantization.')
         else:
