@@ -1,0 +1,29 @@
+#!/bin/bash
+# round 2, one combined GPU call (GPU slots are scarce this round): GPU test suite, smoke, kernel micro-benchmarks, ours-vs-reference kernels,
+# bench (both arms, both workloads), ncu launch list + full captures of the kernels that changed.  Everything lands in gpurun_out/r2_*.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
+echo "== tests"; timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 2>&1 | grep -v "^  \|^$\|Warning\|warn" | cut -c1-400 | tail -120 > gpurun_out/r2_tests.log; tail -70 gpurun_out/r2_tests.log
+echo "== smoke"; python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+echo "== kbench"; timeout 600 python tools/kbench.py --only minmax,hist,lt,lc,ft,quantile,kl,multi --reps 20 > gpurun_out/r2_kbench.txt 2>&1; cat gpurun_out/r2_kbench.txt
+echo "== kbench lc variant 1 (round-1 per-vector operator)"; timeout 200 python - <<'PY' > gpurun_out/r2_kbench_lc_old.txt 2>&1
+import subprocess, sys, os
+sys.path.insert(0, os.getcwd())
+from ppq_b200.ffi import extension
+ext = extension(); ext.set_variant('linear_quant_c', 1)
+sys.argv = ['kbench', '--only', 'lc', '--reps', '20']
+import runpy; runpy.run_path('tools/kbench.py', run_name='__main__')
+PY
+cat gpurun_out/r2_kbench_lc_old.txt
+echo "== vs reference kernels"; timeout 400 python tools/compare_ref_cuda.py 2>&1 | tail -10; cp gpurun_out/vs_reference_kernels.md gpurun_out/r2_vs_reference_kernels.md 2>/dev/null
+echo "== bench reference arm"; timeout 400 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_bench_ref_n1.json 2> gpurun_out/r2_bench_ref.err; echo "ref exit $?"; cut -c1-3000 gpurun_out/r2_bench_ref_n1.json; tail -3 gpurun_out/r2_bench_ref.err
+echo "== bench ours"; timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench.err; echo "bench exit $?"; cut -c1-9000 gpurun_out/r2_bench_n1.json; tail -5 gpurun_out/r2_bench.err
+echo "== bench yolov5s"; timeout 600 python bench.py --workload yolov5s --steps 10 --warmup 3 --no-sweep --no-cpu-baseline > gpurun_out/r2_bench_yolo_n1.json 2> gpurun_out/r2_bench_yolo.err; echo "yolo exit $?"; cut -c1-3500 gpurun_out/r2_bench_yolo_n1.json; tail -3 gpurun_out/r2_bench_yolo.err
+echo "== ncu launch list"; ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches.csv timeout 600 python bench.py --steps 1 --warmup 3 --no-e2e --no-sweep --no-cpu-baseline > gpurun_out/r2_bench_under_ncu.log 2>&1; wc -l gpurun_out/r2_launches.csv
+echo "== ncu captures"
+ncu --set full --clock-control none --import-source on -k regex:select_pass -s 8 -c 3 -f -o gpurun_out/r2_prof_select timeout 300 python tools/kbench.py --only quantile --reps 1 > gpurun_out/r2_ncu_select.log 2>&1; tail -1 gpurun_out/r2_ncu_select.log
+ncu --set full --clock-control none --import-source on -k regex:multi_select_pass0_spec -s 3 -c 1 -f -o gpurun_out/r2_prof_select_spec timeout 300 python tools/kbench.py --only quantile --reps 1 > gpurun_out/r2_ncu_select_spec.log 2>&1; tail -1 gpurun_out/r2_ncu_select_spec.log
+ncu --set full --clock-control none --import-source on -k regex:ew_channel_table -s 2 -c 2 -f -o gpurun_out/r2_prof_lc_table timeout 300 python tools/kbench.py --only lc --reps 1 > gpurun_out/r2_ncu_lc.log 2>&1; tail -1 gpurun_out/r2_ncu_lc.log
+ncu --set full --clock-control none --import-source on -k regex:multi_histogram -s 40 -c 1 -f -o gpurun_out/r2_prof_multi_hist timeout 600 python bench.py --steps 1 --warmup 3 --no-e2e --no-sweep --no-cpu-baseline > gpurun_out/r2_ncu_mh.log 2>&1; tail -1 gpurun_out/r2_ncu_mh.log
+ncu --set full --clock-control none --import-source on -k regex:kl_search -s 1 -c 1 -f -o gpurun_out/r2_prof_kl timeout 300 python tools/kbench.py --only kl --reps 1 > gpurun_out/r2_ncu_kl.log 2>&1; tail -1 gpurun_out/r2_ncu_kl.log
+ls -la gpurun_out | grep r2_
