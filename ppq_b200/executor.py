@@ -262,11 +262,12 @@ class TorchExecutor:
         changed = any(q is not x for q, x in zip(qinputs, tensors))
         if op.weight_cfg is not None:
             w = module.weight
+            wd = w.data                                                  # (`.data` makes a new tensor object on every access)
             wq = self._wq.get(id(module))                                # re-quantised every forward (torch.py:516-518): multi-tensor launch
-            if wq is None: wq = self.quantize_function(w.data, op.weight_cfg)
-            inputs.append(w.data); qinputs.append(wq); cfgs.append(op.weight_cfg)
-            if wq is not w.data:
-                self._swapped[module] = w.data
+            if wq is None: wq = self.quantize_function(wd, op.weight_cfg)
+            inputs.append(wd); qinputs.append(wq); cfgs.append(op.weight_cfg)
+            if wq is not wd:                                             # BAKED / FP32 configs hand the parameter through untouched
+                self._swapped[module] = wd
                 w.data = wq
         if hook is not None: hook.pre_forward_hook(inputs=inputs, quant_inputs=qinputs, quant_configs=cfgs)
         if changed:
