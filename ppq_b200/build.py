@@ -71,7 +71,9 @@ def build_lib(force=False, verbose=False):
                 if verbose and out.strip():
                     print(out)
     if jobs or force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(o) for o in objs):
-        run([NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs + ['-cudart', 'shared', '-Xlinker', '--no-undefined'])
+        # link under a temporary name, then rename: a snapshot of the tree (gpurun) never sees a half-written library
+        run([NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB + '.tmp'] + objs + ['-cudart', 'shared', '-Xlinker', '--no-undefined'])
+        os.replace(LIB + '.tmp', LIB)
     return LIB
 
 
@@ -92,7 +94,7 @@ def build_ext(force=False, verbose=False):
            '-I', INCLUDE, '-I', sysconfig.get_paths()['include'], '-I', '/usr/local/cuda/include']
     for p in inc:
         cmd += ['-isystem', p]
-    cmd += [src, '-o', EXT, '-L', LIBDIR, '-lppq_b200', '-L', torch_lib, '-lc10', '-lc10_cuda', '-ltorch_cpu', '-ltorch_cuda',
+    cmd += [src, '-o', EXT + '.tmp', '-L', LIBDIR, '-lppq_b200', '-L', torch_lib, '-lc10', '-lc10_cuda', '-ltorch_cpu', '-ltorch_cuda',
             '-ltorch', '-ltorch_python', '-L', '/usr/local/cuda/lib64', '-lcudart',
             '-Wl,-rpath,$ORIGIN/_lib', f'-Wl,-rpath,{torch_lib}']
     if verbose:
@@ -100,6 +102,7 @@ def build_ext(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('g++ failed:\n' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
+    os.replace(EXT + '.tmp', EXT)
     return EXT
 
 

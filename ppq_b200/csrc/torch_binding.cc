@@ -27,10 +27,10 @@ namespace {
 
 struct KernelFailure : public std::runtime_error { using std::runtime_error::runtime_error; };
 
-void CheckTensor(const Tensor &t, c10::ScalarType type, const std::string &name) {
-    if (at::typeMetaToScalarType(t.dtype()) != type) throw KernelFailure("Kernel Failure, Invalid dtype of Input tensor: " + name);
-    if (t.numel() == 0) throw KernelFailure("Kernel Failure, Tensor is empty: " + name);
-    if (!t.is_cuda()) throw KernelFailure("Kernel Failure, Tensor is not on a CUDA device: " + name);
+void CheckTensor(const Tensor &t, c10::ScalarType type, const char *name) {         // (const char*: no std::string is built on the success path)
+    if (at::typeMetaToScalarType(t.dtype()) != type) throw KernelFailure(std::string("Kernel Failure, Invalid dtype of Input tensor: ") + name);
+    if (t.numel() == 0) throw KernelFailure(std::string("Kernel Failure, Tensor is empty: ") + name);
+    if (!t.is_cuda()) throw KernelFailure(std::string("Kernel Failure, Tensor is not on a CUDA device: ") + name);
 }
 void CheckStatus(int status, const char *what) {
     if (status != 0) throw KernelFailure(std::string("Kernel Failure, ") + what + ": " + ppq_b200_error_string(status));
