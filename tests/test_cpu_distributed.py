@@ -154,3 +154,20 @@ def test_reduce_fails_on_every_rank_when_one_rank_saw_no_batch(tmp_path):
     mp.spawn(_reduce_worker, args=(world, port, str(tmp_path), 1), nprocs=world, join=True)
     r = [torch.load(tmp_path / f'q{k}.pt') for k in range(world)]
     assert all(x['err'] is not None and 'observed no calibration batch' in x['err'] for x in r)
+
+
+def test_descriptor_stager_cache_is_lru_and_never_stops_caching():
+    """the descriptor cache silently stopped caching after 64 entries; it is an LRU now (host-side logic, no GPU needed)."""
+    sys.path.insert(0, ROOT)
+    from ppq_b200.calibration import DescriptorStager
+    st = DescriptorStager('cpu', 3, cache=4)
+    keys = [tuple((1000 * k + i, 10 + i, i) for i in range(3)) for k in range(6)]
+    first = [st.get(k) for k in keys[:4]]
+    assert all(torch.equal(t, torch.tensor(k, dtype=torch.int64)) for t, k in zip(first, keys))
+    assert st.get(keys[0]) is first[0]                                   # hit: the same tensor, and keys[0] becomes the most recent
+    st.get(keys[4])                                                      # evicts the least recently used = keys[1]
+    assert keys[1] not in st._cache and keys[0] in st._cache and len(st._cache) == 4
+    st.get(keys[5])
+    assert keys[2] not in st._cache and len(st._cache) == 4
+    assert torch.equal(st.get(keys[1]), torch.tensor(keys[1], dtype=torch.int64))       # a miss after eviction is rebuilt and cached again
+    assert keys[1] in st._cache
