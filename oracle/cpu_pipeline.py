@@ -290,19 +290,3 @@ class _Observer:
             put(*kl_search(self.hist, self.hist_scale, 8))
         else:
             put(*mse_search(self.hist, self.hist_scale, self.lo, -128, 127, True, loss_fn=mse_loss_python_twin))
-
-
-def resnet50_cpu_calibration(batch: int, steps: int, seed: int = 0, threads: int = None):
-    """Returns (imgs/s, seconds, number of observed tensors) for `steps` calibration batches (both phases + KL search)."""
-    import torchvision
-    if threads: torch.set_num_threads(threads)
-    torch.manual_seed(seed)
-    model = torchvision.models.resnet50(weights=None)
-    pipe = CpuPipeline(model, torch.zeros(1, 3, 224, 224))
-    pipe.quantize_parameters()
-    g = torch.Generator().manual_seed(seed + 1)
-    data = [torch.rand(batch, 3, 224, 224, generator=g) for _ in range(steps)]
-    t0 = time.perf_counter()
-    scales = pipe.calibrate(data, 'kl')
-    secs = time.perf_counter() - t0
-    return steps * batch / secs, secs, len(scales)
