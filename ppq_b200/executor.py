@@ -108,6 +108,7 @@ class QuantableOperation:
                                                        channel_axis=1 if kind == 'ConvTranspose' else 0)
         self.output_cfg: TensorQuantizationConfig = LinearQuantizationConfig(**act)
         self.consumers: List[tuple] = []                               # (operation, input index)
+        self.stored_weight: Optional[torch.Tensor] = None              # QuantableVariable.stored_value: the fp32 weight behind a baked one
 
     @property
     def input_cfg(self) -> Optional[TensorQuantizationConfig]:
@@ -130,6 +131,7 @@ class TorchExecutor:
         self._names = {id(m): n for n, m in self.model.named_modules()}
         self._hooks, self._collect, self._collected, self._sink = None, False, None, None
         self._tracing, self._wq, self._swapped, self._bypass = True, {}, {}, False
+        self._dequantized = None                                       # [(config, stored state)] while dequantize() is in effect
         self._produced = {}                                            # id(tensor) -> (operation, tensor, version at production)
         self._quant_fn = PPQuantFunction
         for m in self.model.modules():
@@ -379,13 +381,39 @@ class TorchExecutor:
     @torch.no_grad()
     def bake_parameters(self):
         """ParameterBakingPass (optim/baking.py:34-47, IR/quantize.py:98-111): every ACTIVATED / PASSIVE parameter is replaced IN PLACE by its
-        fake-quantised value and its config becomes BAKED / PASSIVE_BAKED, so that later forwards use the value as is."""
+        fake-quantised value and its config becomes BAKED / PASSIVE_BAKED, so that later forwards use the value as is.  The fp32 value stays
+        behind as the operation's `stored_weight` (QuantableVariable.stored_value upstream): dequantize() swaps it back in."""
         for n in self._order:
             op = self.operations[n]
             cfg = op.weight_cfg
             if cfg is None or cfg.state not in (QuantizationStates.ACTIVATED, QuantizationStates.PASSIVE): continue
-            op.module.weight.data = self._quant_fn(op.module.weight.data, cfg)
+            op.stored_weight = op.module.weight.data
+            op.module.weight.data = self._quant_fn(op.stored_weight, cfg)
             cfg.state = QuantizationStates.BAKED if cfg.state == QuantizationStates.ACTIVATED else QuantizationStates.PASSIVE_BAKED
+
+    def dequantize(self):
+        """QuantableOperation.dequantize for every operation (IR/quantize.py:118-141): every config's state is stored and set to FP32, baked
+        parameters are swapped with their stored fp32 values -- the network runs as the original fp32 network."""
+        if self._dequantized is not None: return self
+        self._restore_weights()
+        self._dequantized = []
+        for n in self._order:
+            op = self.operations[n]
+            for cfg in op.input_cfgs + ([op.weight_cfg] if op.weight_cfg is not None else []) + [op.output_cfg]:
+                self._dequantized.append((cfg, cfg.state)); cfg.state = QuantizationStates.FP32
+            if op.stored_weight is not None: op.module.weight.data, op.stored_weight = op.stored_weight, op.module.weight.data
+        return self
+
+    def restore_quantize_state(self):
+        """IR/quantize.py:143-160."""
+        if self._dequantized is None: return self
+        self._restore_weights()
+        for cfg, state in self._dequantized: cfg.state = state
+        for n in self._order:
+            op = self.operations[n]
+            if op.stored_weight is not None: op.module.weight.data, op.stored_weight = op.stored_weight, op.module.weight.data
+        self._dequantized = None
+        return self
 
 
 def _min_scale_of(cfg) -> float:
@@ -497,36 +525,49 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
 
 
 @torch.no_grad()
-def graphwise_error_analyse(executor: TorchExecutor, batches, to_device=None, graphs: bool = False) -> Dict[str, float]:
+def graphwise_error_analyse(executor: TorchExecutor, batches, to_device=None, graphs: bool = False, fetchs: Optional[int] = None,
+                            seed: int = 10086) -> Dict[str, float]:
     """The evaluation loop where fake-quant throughput shows up in user wall-clock (ppq/quantization/analyse/graphwise.py:64-183): run every batch
     through the network twice -- all configs dequantised (fp32) and all configs active -- and report, per quantable operation, the SNR
     mean((q - f)^2) / mean(f^2) per sample, averaged (torch_snr_error, ppq/quantization/measure/norm.py:52-93).  Every activation goes through
     QuantizeTensor_LT and every weight through the multi-tensor QuantizeTensor_LC on each quantised forward.
     graphs=True captures the fp32 forward and the quantised forward (network kernels + ~100 small fake-quant launches + the hooks' bookkeeping)
     into two CUDA graphs on the first batch and replays them for the others (fixed batch shape): the per-call host cost of the drop-in flow
-    (python -> binding -> allocator -> launch, 4.5-5 us x every config x every forward) disappears from the loop."""
-    cfgs = executor.observed_configs_all() + [op.weight_cfg for _, op in executor.quantable_operations() if op.weight_cfg is not None]
-    saved = [c.state for c in cfgs]
-    names = [n for n, op in executor.quantable_operations()]
+    (python -> binding -> allocator -> launch, 4.5-5 us x every config x every forward) disappears from the loop.
+    fetchs=None measures on whole tensors, every quantable operation.  fetchs=4096 follows the reference to the letter: computing operations
+    only (graphwise.py:112-113), `fetchs` elements per sample picked by the reference's seeded linear congruential indexer
+    (utils/fetch.py:4-23, seed 10086) -- pinned against the real function on the B200 (tests/test_gpu_graph_parity.py)."""
+    names = [n for n, op in executor.quantable_operations() if fetchs is None or op.kind in COMPUTING_OP]
     acc = {n: None for n in names}
     count = 0
+    indexers: Dict[tuple, torch.Tensor] = {}
+
+    def sample(t: torch.Tensor) -> torch.Tensor:
+        t = t.flatten(1)
+        if fetchs is None: return t
+        key = (t.shape[-1], t.device)
+        if key not in indexers:
+            idx, sd = [], seed
+            for _ in range(fetchs):
+                idx.append(sd % t.shape[-1]); sd = (0x343FD * sd + 0x269EC3) % (2 << 31)
+            indexers[key] = torch.tensor(idx, dtype=torch.long, device=t.device)
+        return t.index_select(-1, indexers[key])
 
     class Tap:
         def __init__(self, name, store): self.name, self.store = name, store
         def pre_forward_hook(self, **kw): pass
         def post_forward_hook(self, outputs, quant_outputs, quant_configs): self.store[self.name] = quant_outputs[0]
 
-    def dequantised(flag: bool):
-        for c, st in zip(cfgs, saved):
-            c.state = type(c.state)['FP32'] if (flag and getattr(st, 'name', '') in ('ACTIVATED', 'PASSIVE')) else st
-
     def both(x, fp, qt):
-        dequantised(True); executor.forward(x, hooks={n: Tap(n, fp) for n in names})
-        dequantised(False); executor.forward(x, hooks={n: Tap(n, qt) for n in names})
+        executor.dequantize(); executor.forward(x, hooks={n: Tap(n, fp) for n in names})                   # graphwise.py:131-146
+        executor.restore_quantize_state(); executor.forward(x, hooks={n: Tap(n, qt) for n in names})       # :148-165
 
     def snr_all(fp, qt):
-        return torch.stack([(torch.pow(qt[n].flatten(1) - fp[n].flatten(1), 2).sum(dim=-1) / (torch.pow(fp[n].flatten(1), 2).sum(dim=-1) + 1e-7)).mean()
-                            for n in names])
+        out = []
+        for n in names:
+            f, q = sample(fp[n]), sample(qt[n])
+            out.append((torch.pow(q - f, 2).sum(dim=-1) / (torch.pow(f, 2).sum(dim=-1) + 1e-7)).mean())
+        return torch.stack(out)
 
     static_in, graph, fp, qt, static_snr = None, None, {}, {}, None
     try:
@@ -542,8 +583,10 @@ def graphwise_error_analyse(executor: TorchExecutor, batches, to_device=None, gr
                     dev = static_in.device
                     side = torch.cuda.Stream(device=dev)
                     side.wait_stream(torch.cuda.current_stream(dev))
-                    with torch.cuda.stream(side):                         # eager first: lazy initialisation (descriptor tables, cuDNN plans)
-                        both(static_in, {}, {})
+                    with torch.cuda.stream(side):                         # eager first: lazy initialisation (descriptor tables, cuDNN plans, indexers)
+                        wf, wq_ = {}, {}
+                        both(static_in, wf, wq_); snr_all(wf, wq_)
+                        del wf, wq_
                     torch.cuda.current_stream(dev).wait_stream(side)
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
@@ -556,7 +599,7 @@ def graphwise_error_analyse(executor: TorchExecutor, batches, to_device=None, gr
             acc_t = snr if count == 0 else acc_t + snr                     # noqa: F821 (defined on the first iteration)
             count += 1
     finally:
-        dequantised(False)
+        executor.restore_quantize_state()
     if count == 0: return {n: 0.0 for n in names}
     vals = (acc_t / count).tolist()
     del acc

@@ -146,7 +146,7 @@ def snapshot(graph):
     return rows
 
 
-def run_reference_pipeline(ppq, spec, params, data, method, device='cpu', cuda_kernel=False):
+def run_reference_pipeline(ppq, spec, params, data, method, device='cpu', cuda_kernel=False, analyse=False):
     """The unmodified reference: TRT_INT8 quantizer -> its own pass list -> snapshots + the quantised graph's output on data[0].
     With cuda_kernel=True the passes run inside `with ENABLE_CUDA_KERNEL():` (whatever extension ppq.core.ffi currently serves)."""
     import contextlib
@@ -179,4 +179,8 @@ def run_reference_pipeline(ppq, spec, params, data, method, device='cpu', cuda_k
         res['final'] = snapshot(graph)
         res['output'] = ex.forward(batches[0])[0].detach().cpu().numpy().copy()
         res['baked'] = {k: graph.variables[k].value.detach().cpu().numpy().copy() for k in params if k.endswith('.w')}
+        if analyse:                                                      # the reference's own evaluation loop (quantization/analyse/graphwise.py:64-183)
+            from ppq.quantization.analyse import graphwise_error_analyse
+            res['graphwise'] = graphwise_error_analyse(graph=graph, running_device=device, dataloader=batches, collate_fn=None, method='snr',
+                                                       steps=len(batches), verbose=False)
     return res

@@ -184,6 +184,7 @@ def test_parameter_baking_states_values_and_no_requantisation(env):
     ops['conv3#0'].weight_cfg.master_by = ops['conv2#0'].weight_cfg        # a passive parameter config: shares conv2's per-channel scales (16 channels each)
     assert ops['conv3#0'].weight_cfg.state == S.PASSIVE and ops['conv3#0'].weight_cfg.scale is ops['conv2#0'].weight_cfg.scale
     weighted = {n: op for n, op in ops.items() if op.weight_cfg is not None}
+    fp32 = {n: op.module.weight.data.clone() for n, op in weighted.items()}
     want = {n: PPQuantFunction(op.module.weight.data, op.weight_cfg).clone() for n, op in weighted.items()}
     assert len(ex._quantize_all_weights()) == len(weighted) - 1            # before baking: every ACTIVATED weight is re-quantised per forward (one launch)
     ex._restore_weights()
@@ -199,3 +200,34 @@ def test_parameter_baking_states_values_and_no_requantisation(env):
     ex.bake_parameters()                                                   # idempotent: BAKED configs are skipped
     for n, op in weighted.items():
         assert np.array_equal(bits(op.module.weight.data.cpu().numpy()), bits(want[n].cpu().numpy())), n
+    # dequantize() / restore_quantize_state() (IR/quantize.py:118-160): the fp32 weights come back from `stored_value`, every config reads FP32
+    ex.dequantize()
+    for n, op in weighted.items():
+        assert op.weight_cfg.state == S.FP32 and op.output_cfg.state == S.FP32
+        assert np.array_equal(bits(op.module.weight.data.cpu().numpy()), bits(fp32[n].cpu().numpy())), n
+    ex.restore_quantize_state()
+    for n, op in weighted.items():
+        assert op.weight_cfg.state == (S.PASSIVE_BAKED if n == 'conv3#0' else S.BAKED)
+        assert np.array_equal(bits(op.module.weight.data.cpu().numpy()), bits(want[n].cpu().numpy())), n
+
+
+def test_graphwise_error_analyse_equals_the_reference_function(env):
+    """The evaluation loop: the reference's own graphwise_error_analyse on its quantised graph (our kernels installed) vs ours on the
+    equivalent module with bit-identical configs -- same operations, same seeded sample of 4096 elements per image, same SNR."""
+    import ppq_b200.install as inst
+    from ppq_b200.executor import calibrate_arena, graphwise_error_analyse
+    inst.install(replace_observers=False)
+    try:
+        want = netspec.run_reference_pipeline(env['ppq'], env['spec'], env['params'], env['data'], 'kl', device='cuda', cuda_kernel=True, analyse=True)
+    finally:
+        inst.uninstall()
+    ex, batches = our_executor(env)
+    calibrate_arena(ex, batches, method='kl')
+    ex.align_quantization(); ex.bake_parameters()
+    check_against(ex, env, want['final'], 'analyse/final')
+    got = graphwise_error_analyse(ex, batches, fetchs=4096)
+    assert sorted(got) == sorted(k + '#0' for k in want['graphwise']), (sorted(got), sorted(want['graphwise']))
+    for k, v in want['graphwise'].items():
+        assert abs(got[k + '#0'] - v) <= 1e-6 + 2e-4 * abs(v), (k, got[k + '#0'], v)
+    full = graphwise_error_analyse(ex, batches)                            # whole tensors, every operation: same order of magnitude, all below the 0.1 bar
+    assert len(full) == len(ex.quantable_operations()) and all(0 <= e < 0.1 for e in full.values())
