@@ -437,7 +437,7 @@ def run_e2e(args, device, world, rank):
     except Exception as e:                                               # executor lands after the kernels; never silently fake a number
         return {'value': None, 'unit': UNIT, 'unavailable': f'{type(e).__name__}: {e}'}
     return e2e_calibration_benchmark(batch=args.batch, batches=max(1, SAMPLES_PER_GPU // args.batch), steps=args.e2e_steps,
-                                     warmup=args.warmup, device=device, world=world, seed=rank)
+                                     warmup=args.warmup, device=device, world=world, seed=rank, channels_last=args.e2e_channels_last)
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port of the reference CPU path)
@@ -571,6 +571,7 @@ def main():
     ap.add_argument('--rotate', type=int, default=4, help='distinct activation sets cycled through (each > L2)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--e2e-steps', type=int, default=3, help='timed end-to-end calibrations of 512 samples (each ~0.14 s)')
+    ap.add_argument('--e2e-channels-last', action='store_true', help='run the torch network of the e2e arm in NHWC (the hot path reads dense tensors in storage order)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-sweep', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='profiling runs only')

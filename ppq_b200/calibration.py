@@ -71,6 +71,15 @@ def gather_in_sample_order(local: torch.Tensor, group=None) -> torch.Tensor:
     return torch.stack(rows, dim=1)
 
 
+def is_dense(t: torch.Tensor) -> bool:
+    """Contiguous in some memory format (NCHW or channels_last): per-tensor collectors and element-wise operators are order-independent, so
+    such a tensor is processed in storage order without a copy."""
+    if t.is_contiguous(): return True
+    if t.dim() == 4: return t.is_contiguous(memory_format=torch.channels_last)
+    if t.dim() == 5: return t.is_contiguous(memory_format=torch.channels_last_3d)
+    return False
+
+
 def shard_indices(num_samples: int, rank: int, world_size: int) -> range:
     """Sample partition of SURVEY §8e: rank r takes samples r, r + R, r + 2R, ..."""
     return range(rank, num_samples, world_size)
@@ -159,8 +168,8 @@ class ArenaCalibrator:
             assert len(tensors) == self.T, f'expected {self.T} tensors per forward, got {len(tensors)}'
             slots = range(self.T)
         for t in tensors:
-            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
-                raise RuntimeError('ArenaCalibrator needs contiguous fp32 CUDA tensors')
+            if not (t.is_cuda and t.dtype == torch.float32 and is_dense(t)):
+                raise RuntimeError('ArenaCalibrator needs dense (contiguous or channels_last) fp32 CUDA tensors')
         key = tuple((t.data_ptr(), t.numel(), i) for t, i in zip(tensors, slots))
         return self._stager.get(key), max(k[1] for k in key)
 
@@ -429,8 +438,13 @@ class MultiWeightQuantizer:
         self.ext = extension()
         self.quant_min, self.quant_max, self.rounding = quant_min, quant_max, rounding
         self.per_tensor = channel_axis is None
-        self.weights = [w.contiguous() for w in weights]
-        self.outputs = [torch.empty_like(w) for w in self.weights]
+
+        def rows_in_storage_order(w):
+            # axis-0 channels of a dense tensor whose dim 0 is outermost in memory (NCHW or channels_last weights): the storage already is [C, epc]
+            return channel_axis is not None and w.dim() > 0 and channel_axis % w.dim() == 0 and is_dense(w) and w.numel() > 0 and \
+                w.stride(0) == w.numel() // w.shape[0]
+        self.weights = [w if (is_dense(w) if self.per_tensor else rows_in_storage_order(w)) else w.contiguous() for w in weights]
+        self.outputs = [torch.empty_like(w) for w in self.weights]            # preserve_format: same strides as the input
         self.scales = [s.contiguous() for s in scales]
         self.offsets = [o.contiguous() for o in offsets]
         rows = []

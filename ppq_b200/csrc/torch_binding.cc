@@ -39,6 +39,9 @@ void CheckSize(const Tensor &t) {
     if (t.numel() > 0x7fffffffLL) throw KernelFailure("There are too many element in your tensor(more than 2*10^9)");
 }
 void *Stream() { return (void *)at::cuda::getCurrentCUDAStream().stream(); }
+// Per-TENSOR operators are order-independent (element-wise maps, reductions, histograms, order statistics): any dense layout (e.g. a
+// channels_last activation) is processed in storage order, without the NCHW copy `.contiguous()` would make; at::empty_like keeps the strides.
+Tensor Dense(const Tensor &t) { return t.is_non_overlapping_and_dense() ? t : t.contiguous(); }
 const float *F(const Tensor &t) { return t.data_ptr<float>(); }
 
 struct Geometry { int64_t epc; int C; };
@@ -63,7 +66,7 @@ Tensor QuantizeTensor_LT(const Tensor &value, const Tensor &scale, const Tensor 
     CheckTensor(offset, at::kFloat, "Offset(Expect to be FP32)");
     CheckSize(value);
     const c10::cuda::CUDAGuard guard(value.device());
-    auto v = value.contiguous();
+    auto v = Dense(value);
     Tensor out = at::empty_like(v);
     CheckStatus(ppq_b200_linear_quant_t(F(v), out.data_ptr<float>(), v.numel(), F(scale), F(offset), clip_min, clip_max, rounding,
                                         Stream()), "QuantizeTensor_LT");
@@ -118,7 +121,7 @@ Tensor QuantizeTensor_FT(const Tensor &value, const Tensor &scale, const Tensor 
     CheckTensor(scale, at::kFloat, "Scale(Expect to be FP32)");
     CheckTensor(offset, at::kFloat, "Offset(Expect to be FP32)");
     const c10::cuda::CUDAGuard guard(value.device());
-    auto v = value.contiguous();
+    auto v = Dense(value);
     Tensor out = at::empty_like(v);
     CheckStatus(ppq_b200_float_quant_t(F(v), out.data_ptr<float>(), v.numel(), F(scale), F(offset), exponent, mantissa, clip_min,
                                        clip_max, rounding, Stream()), "QuantizeTensor_FT");
@@ -146,7 +149,7 @@ void Histogram_T(const Tensor &value, const float hist_scale, const bool clip_ou
     CheckTensor(value, at::kFloat, "Value(Expect to be FP32)");
     CheckTensor(hist, at::kInt, "Histogram(Expect to be INT32)");
     const c10::cuda::CUDAGuard guard(value.device());
-    auto v = value.contiguous();
+    auto v = Dense(value);
     CheckStatus(ppq_b200_histogram_t(F(v), v.numel(), hist_scale, clip_outliers, hist.data_ptr<int>(), hist.numel(), Stream()),
                 "Histogram_T");
 }
@@ -155,7 +158,7 @@ void Histogram_Asymmetric_T(const float min, const float max, const Tensor &valu
     CheckTensor(value, at::kFloat, "Value(Expect to be FP32)");
     CheckTensor(hist, at::kInt, "Histogram(Expect to be INT32)");
     const c10::cuda::CUDAGuard guard(value.device());
-    auto v = value.contiguous();
+    auto v = Dense(value);
     CheckStatus(ppq_b200_histogram_asym_t(F(v), v.numel(), min, max, clip_outliers, hist.data_ptr<int>(), hist.numel(), Stream()),
                 "Histogram_Asymmetric_T");
 }
@@ -188,7 +191,7 @@ void MinMax_T(const Tensor &value, Tensor &minmax) {
     CheckTensor(minmax, at::kFloat, "MinMax(Expect to be FP32)");
     if (minmax.numel() != 2) throw KernelFailure("Kernel Failure, MinMax buffer must hold 2 floats.");
     const c10::cuda::CUDAGuard guard(value.device());
-    auto v = value.contiguous();
+    auto v = Dense(value);
     CheckStatus(ppq_b200_minmax_t(F(v), v.numel(), minmax.data_ptr<float>(), Stream()), "MinMax_T");
 }
 void MinMax_C(const Tensor &value, const int channel_axis, Tensor &mins, Tensor &maxs) {
@@ -206,7 +209,7 @@ void Histogram_T_DeviceScale(const Tensor &value, const Tensor &hist_scale, cons
     CheckTensor(hist_scale, at::kFloat, "HistScale(Expect to be FP32)");
     CheckTensor(hist, at::kInt, "Histogram(Expect to be INT32)");
     const c10::cuda::CUDAGuard guard(value.device());
-    auto v = value.contiguous();
+    auto v = Dense(value);
     CheckStatus(ppq_b200_histogram_t_dscale(F(v), v.numel(), F(hist_scale), clip_outliers, hist.data_ptr<int>(), hist.numel(), Stream()),
                 "Histogram_T_DeviceScale");
 }

@@ -123,8 +123,14 @@ class QuantableOperation:
 
 
 class TorchExecutor:
-    def __init__(self, model: torch.nn.Module, example_input: torch.Tensor, fuse_bn: bool = True):
+    def __init__(self, model: torch.nn.Module, example_input: torch.Tensor, fuse_bn: bool = True, channels_last: bool = False):
+        """channels_last=True runs the torch network in NHWC (cuDNN's native tensor-core layout).  The hot path does not care: per-tensor
+        collectors and fake-quant are order-independent and read dense tensors in storage order; axis-0 weight rows stay contiguous."""
         self.model = fuse_conv_bn(model) if fuse_bn else model.eval()
+        self._channels_last = channels_last
+        if channels_last:
+            self.model = self.model.to(memory_format=torch.channels_last)
+            if example_input.dim() == 4: example_input = example_input.contiguous(memory_format=torch.channels_last)
         self.operations: Dict[str, QuantableOperation] = {}
         self._order: List[str] = []
         self._calls: Dict[int, int] = {}
@@ -303,6 +309,7 @@ class TorchExecutor:
         valid for tensors the network does not overwrite in place; `sink(k, tensor)` observes the k-th tensor immediately (a sink that
         returns False leaves the tensor in the collected list instead)."""
         self._hooks, self._collect, self._sink = hooks, collect or sink is not None, sink
+        if self._channels_last and inputs.dim() == 4: inputs = inputs.contiguous(memory_format=torch.channels_last)
         self._begin()
         try:
             out = self.model(inputs)
@@ -388,7 +395,9 @@ class TorchExecutor:
             cfg = op.weight_cfg
             if cfg is None or cfg.state not in (QuantizationStates.ACTIVATED, QuantizationStates.PASSIVE): continue
             op.stored_weight = op.module.weight.data
-            op.module.weight.data = self._quant_fn(op.stored_weight, cfg)
+            baked = self._quant_fn(op.stored_weight, cfg)
+            if self._channels_last and baked.dim() == 4: baked = baked.contiguous(memory_format=torch.channels_last)
+            op.module.weight.data = baked
             cfg.state = QuantizationStates.BAKED if cfg.state == QuantizationStates.ACTIVATED else QuantizationStates.PASSIVE_BAKED
 
     def dequantize(self):
@@ -459,7 +468,7 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
     graph and replays it for every batch (fixed batch shape).  Measured on B200 (ResNet-50, 8 x 32 images): capture + instantiate
     costs more than it saves at 8-16 batches per phase (1330 vs 3124 imgs/s end to end), so it is off by default; it pays off for long
     calibration sets or when the same graph is reused across calls."""
-    from .calibration import ArenaCalibrator
+    from .calibration import ArenaCalibrator, is_dense
     cfgs = executor.observed_configs()
     for c in cfgs: c.observer_algorithm = method
     if iter(batches) is batches: batches = list(batches)                  # a one-shot iterator would leave phase 2 without data
@@ -496,7 +505,7 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
             if to_device is not None and not overlapped: x = to_device(x)
             if deferred is True:
                 _, tensors = executor.forward(x, collect=True)
-                cal.observe([t if t.is_contiguous() else t.contiguous() for t in tensors])
+                cal.observe([t if is_dense(t) else t.contiguous() for t in tensors])
                 del tensors
             elif deferred == 'auto':
                 if mutated is None:                                       # probe forward: observe immediately, remember versions
@@ -505,7 +514,7 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
                     def probe(k, t):
                         cal.observe_one(k, t); seen.append((t, t._version))
                     executor.forward(x, sink=probe)
-                    mutated = {k for k, (t, v) in enumerate(seen) if t._version != v or not t.is_contiguous()}
+                    mutated = {k for k, (t, v) in enumerate(seen) if t._version != v or not is_dense(t)}
                     del seen
                 else:
                     def sink(k, t):
@@ -606,7 +615,8 @@ def graphwise_error_analyse(executor: TorchExecutor, batches, to_device=None, gr
     return dict(zip(names, vals))
 
 
-def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int, device, world: int = 1, seed: int = 0, graphs: bool = False):
+def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int, device, world: int = 1, seed: int = 0, graphs: bool = False,
+                              channels_last: bool = False):
     """bench.py's `e2e`: ResNet-50 (random init, BN folded) calibrated end to end through the public API -- `batches` x `batch` images in pinned
     host memory (this rank's share of the calibration set), H2D copy of every batch inside the timed region (both phases), torch forward with
     per-forward weight fake-quant, multi-tensor collectors, the two all-reduces, on-device KL search and a D2H read of the resulting scales.
@@ -617,7 +627,7 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
     model = torchvision.models.resnet50(weights=None).eval()
-    ex = TorchExecutor(model.to(device), torch.zeros(2, 3, 224, 224, device=device))
+    ex = TorchExecutor(model.to(device), torch.zeros(2, 3, 224, 224, device=device), channels_last=channels_last)
     ex.quantize_parameters()
     g = torch.Generator().manual_seed(1000 + seed)                         # every rank calibrates its OWN shard of the sample set
     host = [torch.rand(batch, 3, 224, 224, generator=g).pin_memory() for _ in range(batches)]
@@ -666,7 +676,7 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
             for x in prefetch_to_device(host, to_dev, device):
                 if bypass:
                     ex._bypass = True
-                    try: ex.model(x)
+                    try: ex.model(x.contiguous(memory_format=torch.channels_last) if channels_last else x)
                     finally: ex._bypass = False
                 else:
                     ex.forward(x, sink=lambda k, t: True)                 # hooks + per-forward weight fake-quant, no collector launch
@@ -682,7 +692,7 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
             'ms_per_step': round(total, 3), 'steps': steps, 'step': f'one whole calibration: {batches} batches x {batch} images, both phases',
             'step_ms': {'min': round(min(step_ms), 3), 'median': round(sorted(step_ms)[len(step_ms) // 2], 3), 'max': round(max(step_ms), 3)},
             'warmup_calibrations_ms': [round(w, 2) for w in warm],
-            'observed_tensors': int(scales.numel()), 'cuda_graphs': graphs,
+            'observed_tensors': int(scales.numel()), 'cuda_graphs': graphs, 'channels_last': channels_last,
             'breakdown_ms_per_batch_pass': {'forward_fp32_cudnn': round(pure / nb2, 3), 'hooks_and_weight_fakequant': round((hooked - pure) / nb2, 3),
                                             'collectors_exchange_search': round((total - hooked) / nb2, 3),
                                             'h2d_copy_overlapped': round(h2d / nb2, 3), 'total': round(total / nb2, 3)},

@@ -193,3 +193,38 @@ def test_executor_calibration_paths_agree(ext):
     yf = ex2.forward(x)
     snr = float(((yq - yf) ** 2).sum() / (yf ** 2).sum())
     assert 0 < snr < 0.1                                                    # tests/test_block.py:35-40 bar: SNR(quantised vs fp32) < 0.1
+
+
+def test_channels_last_network_is_read_in_storage_order(ext, oracle):
+    """A network run in NHWC (cuDNN's native layout): per-tensor collectors / fake-quant are order-independent and read the dense tensors as they lie;
+    axis-0 weight rows stay contiguous in channels_last, so the multi-tensor weight fake-quant needs no copy either.  Same statistics as NCHW up to
+    the convolutions' own rounding; element-wise results identical."""
+    import torchvision
+    from ppq_b200.calibration import MultiWeightQuantizer
+    from ppq_b200.executor import TorchExecutor, calibrate_arena
+    g = torch.Generator(device='cuda').manual_seed(3)
+    x = torch.randn(8, 24, 14, 14, device='cuda', generator=g)
+    xc = x.contiguous(memory_format=torch.channels_last)
+    s, o = torch.tensor([0.03], device='cuda'), torch.tensor([0.0], device='cuda')
+    y, yc = ext.QuantizeTensor_LT(x, s, o, -128, 127, 0), ext.QuantizeTensor_LT(xc, s, o, -128, 127, 0)
+    assert yc.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, yc)          # same values at the same logical positions, no layout change
+    assert torch.equal(ext.Quantile_T(x, 0.99), ext.Quantile_T(xc, 0.99))
+    mm, mmc = torch.empty(2, device='cuda'), torch.empty(2, device='cuda')
+    ext.MinMax_Init(mm[0:1], mm[1:2]); ext.MinMax_Init(mmc[0:1], mmc[1:2]); ext.MinMax_T(x, mm); ext.MinMax_T(xc, mmc)
+    assert torch.equal(mm, mmc)
+    w = torch.randn(32, 16, 3, 3, device='cuda', generator=g) * 0.1
+    wc = w.contiguous(memory_format=torch.channels_last)
+    sc = (w.abs().amax(dim=(1, 2, 3)) / 127).contiguous(); oc = torch.zeros_like(sc)
+    out = MultiWeightQuantizer([wc, w], [sc, sc], [oc, oc], channel_axis=0)()
+    assert out[0].is_contiguous(memory_format=torch.channels_last) and torch.equal(out[0], out[1])
+    assert np.array_equal(bits(out[1]), oracle.linear_quant_c(w.cpu().numpy(), sc.cpu().numpy(), oc.cpu().numpy(), 0, -128, 127).view(np.uint32))
+    torch.manual_seed(7)
+    data = [torch.rand(4, 3, 64, 64, device='cuda') for _ in range(8)]
+
+    def scales(channels_last):
+        torch.manual_seed(11)
+        ex = TorchExecutor(torchvision.models.resnet18(weights=None).cuda(), torch.zeros(2, 3, 64, 64, device='cuda'), channels_last=channels_last)
+        ex.quantize_parameters()
+        return calibrate_arena(ex, data, method='minmax').scale, len(ex.observed_configs_all())
+    (a, na), (b, nb) = scales(False), scales(True)
+    assert na == nb and torch.allclose(a, b, rtol=2e-3, atol=1e-7), (a - b).abs().max()
