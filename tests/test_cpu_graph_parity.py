@@ -151,3 +151,27 @@ def test_fixture_is_what_the_reference_produces_today(fx):
             assert (row['op'], row['var'], row['state'], row['dominator']) == (r['op'], r['var'], r['state'], r['dominator'])
             if row['scale'] is not None: assert np.array_equal(bits(row['scale']), bits(z[r['scale']]))
     assert np.array_equal(bits(res['output']), bits(z['percentile.output']))
+
+
+def test_executor_dequantize_and_restore_swap_states_and_stored_weights(fx):
+    """IR/quantize.py:118-160 as mirrored by the executor: dequantize() stores every config's state, sets FP32 and swaps baked parameters with their
+    stored fp32 values; restore_quantize_state() undoes both (host logic only: no kernel involved)."""
+    from ppq_b200.core import QuantizationStates as S
+    from ppq_b200.executor import TorchExecutor
+    _, meta = fx
+    spec, params, data = net_and_data(meta)
+    ex = TorchExecutor(netspec.SpecNet(spec, params), data[0], fuse_bn=False)
+    ops = dict(ex.quantable_operations())
+    conv = ops['conv1#0']
+    fp32 = conv.module.weight.data.clone()
+    baked = fp32 * 0.5                                                     # stand-in for the fake-quantised value
+    conv.stored_weight, conv.module.weight.data, conv.weight_cfg.state = conv.module.weight.data, baked, S.BAKED
+    before = {(n, i): c.state for n, op in ops.items() for i, c in enumerate(op.input_cfgs + [op.output_cfg])}
+    ex.dequantize()
+    assert all(c.state == S.FP32 for op in ops.values() for c in op.input_cfgs + [op.output_cfg]) and conv.weight_cfg.state == S.FP32
+    assert torch.equal(conv.module.weight.data, fp32) and torch.equal(conv.stored_weight, baked)
+    ex.dequantize()                                                        # idempotent
+    assert torch.equal(conv.module.weight.data, fp32)
+    ex.restore_quantize_state()
+    assert {(n, i): c.state for n, op in ops.items() for i, c in enumerate(op.input_cfgs + [op.output_cfg])} == before
+    assert conv.weight_cfg.state == S.BAKED and torch.equal(conv.module.weight.data, baked) and torch.equal(conv.stored_weight, fp32)
