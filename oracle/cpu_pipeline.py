@@ -33,7 +33,8 @@ ELEMENTWISE = {'Add', 'Sub', 'Sum'}
 
 def _kind(m):
     table = {torch.nn.Conv2d: 'Conv', torch.nn.Linear: 'Gemm', torch.nn.ReLU: 'Relu', torch.nn.ReLU6: 'Clip', torch.nn.MaxPool2d: 'MaxPool',
-             torch.nn.AdaptiveAvgPool2d: 'GlobalAveragePool', torch.nn.AvgPool2d: 'AveragePool', torch.nn.Flatten: 'Flatten'}
+             torch.nn.AdaptiveAvgPool2d: 'GlobalAveragePool', torch.nn.AvgPool2d: 'AveragePool', torch.nn.Flatten: 'Flatten',
+             torch.nn.Sigmoid: 'Sigmoid'}
     for t in type(m).__mro__:
         if t in table: return table[t]
         if t.__name__ in ('Add', 'Concat') and t.__module__ != 'torch.nn.modules.module': return t.__name__      # element-wise ops written as modules
@@ -235,15 +236,21 @@ class CpuPipeline:
     @torch.no_grad()
     def align(self):
         for op in self.ops:
-            if op.kind not in ELEMENTWISE or not op.ins: continue
-            lo = hi = 0
-            for c in op.ins:
-                hi = max(hi, (c.scale * (127 - c.offset)).item()); lo = min(lo, (c.scale * (-128 - c.offset)).item())
-            s, o = minmax_to_scale_offset(lo, hi, -128, 127, True)
-            master = op.ins[0]
-            master.parent, master.state = master, 'PASSIVE'
-            master._scale, master._offset = torch.tensor(s, dtype=torch.float32), torch.tensor(float(o), dtype=torch.float32)
-            for c in op.ins[1:]: c.slave_of(master)
+            if not op.ins: continue
+            if op.kind in ELEMENTWISE:                                                         # 'Align to Large' (refine.py:443-482)
+                lo = hi = 0
+                for c in op.ins:
+                    hi = max(hi, (c.scale * (127 - c.offset)).item()); lo = min(lo, (c.scale * (-128 - c.offset)).item())
+                s, o = minmax_to_scale_offset(lo, hi, -128, 127, True)
+                master = op.ins[0]
+                master.parent, master.state = master, 'PASSIVE'
+                master._scale, master._offset = torch.tensor(s, dtype=torch.float32), torch.tensor(float(o), dtype=torch.float32)
+                for c in op.ins[1:]: c.slave_of(master)
+            elif op.kind == 'Concat':                                                          # 'Align to Output' (refine.py:484-496)
+                master = op.out
+                for c in op.ins: c.slave_of(master)
+            else:
+                continue
             for src in op.sources:
                 if src is not None: src.out.slave_of(master)                                   # force_alignment_overlap = True
 

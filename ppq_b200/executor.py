@@ -71,6 +71,7 @@ PASSIVE_OPERATIONS = {'MaxPool', 'GlobalMaxPool', 'Reshape', 'Flatten', 'Identit
                       'Interp', 'Squeeze', 'Unsqueeze'}
 ACTIVATION_FUSION_TYPES = {'Relu', 'Clip', 'Swish', 'SoftPlus', 'Sigmoid', 'Gelu'}     # TensorRTQuantizer.py:103-104
 ELEMENTWISE_ALIGNMENT_TYPES = {'Add', 'Sub', 'Sum'}                                     # core/common.py:60-63
+CONCAT_ALIGNMENT_TYPES = {'Concat'}
 
 
 def fuse_conv_bn(model: torch.nn.Module) -> torch.nn.Module:
@@ -350,33 +351,43 @@ class TorchExecutor:
 
     @torch.no_grad()
     def align_quantization(self, force_overlap: bool = True):
-        """QuantAlignmentPass for element-wise operations, 'Align to Large' (optim/refine.py:443-482, 498-546; the default setting
-        api/setting.py:251-256 has force_alignment_overlap = True): the first input config becomes the PASSIVE master of the op's
-        inputs with the scale of the widest input range; with force_overlap (or a single consumer) the producers' output configs are
-        slaved to it as well, so the tensors are quantised once, with the shared scale, where they are produced."""
+        """QuantAlignmentPass with the default setting (optim/refine.py:443-546; api/setting.py:251-256: element-wise 'Align to Large', concat
+        'Align to Output', pooling 'None', force_alignment_overlap = True).
+        Element-wise (Add / Sub / Sum): the first input config becomes the PASSIVE master of the op's inputs with the scale of the widest input
+        range.  Concat: the output config is the master, every input config is slaved to it.  With force_overlap (or a single consumer) the
+        producers' output configs are slaved to the master as well, so the tensors are quantised once, with the shared scale, where they are
+        produced."""
         from .core import QuantizationProperty as P
         ext = self._ext()
         for n in self._order:
             op = self.operations[n]
-            if op.kind not in ELEMENTWISE_ALIGNMENT_TYPES or not op.input_cfgs: continue
-            master = op.input_cfgs[0]
-            los, his = [], []
-            for cfg in op.input_cfgs:
-                if cfg.state == QuantizationStates.FP32 or cfg.policy.has_property(P.FLOATING): continue
-                assert cfg.policy.has_property(P.PER_TENSOR), 'Quant Alignment can only happen with per tensor quantization.'
-                s, o = cfg.scale.float().reshape(()), cfg.offset.float().reshape(())
-                los.append(s * (cfg.quant_min - o)); his.append(s * (cfg.quant_max - o))     # fp32 products, as upstream's tensors
-            zero = torch.zeros((), dtype=torch.float32, device=master.scale.device)
-            lo = torch.minimum(torch.stack(los).min(), zero).reshape(1)                     # global_min / global_max start from 0
-            hi = torch.maximum(torch.stack(his).max(), zero).reshape(1)
-            scale, offset = ext.MinMax_To_Scale_Offset(lo, hi, 1, master.quant_min, master.quant_max, master.policy.has_property(P.SYMMETRICAL),
-                                                       master.policy.has_property(P.POWER_OF_2), _min_scale_of(master))
-            master._dominator = master
-            master.state = QuantizationStates.PASSIVE
-            master.scale, master.offset = scale.squeeze(0), offset.squeeze(0)
-            for slave in op.input_cfgs[1:]:
-                slave.master_by = master
-            for src in self._upstream(op):
+            if not op.input_cfgs: continue
+            if op.kind in ELEMENTWISE_ALIGNMENT_TYPES:
+                master = op.input_cfgs[0]
+                los, his = [], []
+                for cfg in op.input_cfgs:
+                    if cfg.state == QuantizationStates.FP32 or cfg.policy.has_property(P.FLOATING): continue
+                    assert cfg.policy.has_property(P.PER_TENSOR), 'Quant Alignment can only happen with per tensor quantization.'
+                    s, o = cfg.scale.float().reshape(()), cfg.offset.float().reshape(())
+                    los.append(s * (cfg.quant_min - o)); his.append(s * (cfg.quant_max - o))     # fp32 products, as upstream's tensors
+                zero = torch.zeros((), dtype=torch.float32, device=master.scale.device)
+                lo = torch.minimum(torch.stack(los).min(), zero).reshape(1)                     # global_min / global_max start from 0
+                hi = torch.maximum(torch.stack(his).max(), zero).reshape(1)
+                scale, offset = ext.MinMax_To_Scale_Offset(lo, hi, 1, master.quant_min, master.quant_max, master.policy.has_property(P.SYMMETRICAL),
+                                                           master.policy.has_property(P.POWER_OF_2), _min_scale_of(master))
+                master._dominator = master
+                master.state = QuantizationStates.PASSIVE
+                master.scale, master.offset = scale.squeeze(0), offset.squeeze(0)
+                for slave in op.input_cfgs[1:]:
+                    slave.master_by = master
+            elif op.kind in CONCAT_ALIGNMENT_TYPES:                                            # align_to_output (refine.py:484-496)
+                master = op.output_cfg
+                for slave in op.input_cfgs:
+                    if slave.policy.has_property(P.FLOATING) or slave.state == QuantizationStates.FP32: continue
+                    slave.master_by = master
+            else:
+                continue
+            for src in self._upstream(op):                                                      # override the producers' configs (:537-546)
                 if len(src.consumers) != 1 and not force_overlap: continue
                 if any(dst is op for dst, _ in src.consumers): src.output_cfg.master_by = master
 

@@ -22,21 +22,16 @@ import torch
 import netspec
 import refppq
 
-NET, PARAM_SEED, DATA_SEED, STEPS, BATCH = 'tinyres', 7, 11, 8, 4
-METHODS = ('kl', 'minmax', 'percentile', 'mse')
+NETS = {'tinyres': ('kl', 'minmax', 'percentile', 'mse'), 'tinycat': ('kl', 'percentile')}
+PARAM_SEED, DATA_SEED, STEPS, BATCH = 7, 11, 8, 4
 
 
-def main():
-    ppq = refppq.load()
-    assert ppq is not None and refppq.root() == '/root/reference', 'generate fixtures from the read-only reference checkout'
-    from ppq.core import PPQ_CONFIG
-    assert PPQ_CONFIG.USING_CUDA_KERNEL is False
-    torch.set_num_threads(1)                                   # deterministic reductions
-    spec = netspec.SPECS[NET]
+def generate(ppq, net, methods):
+    spec = netspec.SPECS[net]
     params = netspec.make_params(spec, PARAM_SEED)
-    data = netspec.make_data(NET, DATA_SEED, STEPS, BATCH)
-    arrays, meta = {}, dict(net=NET, param_seed=PARAM_SEED, data_seed=DATA_SEED, steps=STEPS, batch=BATCH, methods={})
-    for method in METHODS:
+    data = netspec.make_data(net, DATA_SEED, STEPS, BATCH)
+    arrays, meta = {}, dict(net=net, param_seed=PARAM_SEED, data_seed=DATA_SEED, steps=STEPS, batch=BATCH, methods={})
+    for method in methods:
         res = netspec.run_reference_pipeline(ppq, spec, params, data, method)
         entry = {'passes': res['passes']}
         for stage in ('calibrated', 'final'):
@@ -54,9 +49,18 @@ def main():
         for k, v in res['baked'].items(): arrays[f'{method}.baked.{k}'] = v
         meta['methods'][method] = entry
     arrays['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
-    out = os.path.join(HERE, 'graph_pipeline.npz')
+    out = os.path.join(HERE, 'graph_pipeline.npz' if net == 'tinyres' else f'graph_pipeline_{net}.npz')
     np.savez_compressed(out, **arrays)
-    print(out, os.path.getsize(out), 'bytes;', {m: sum(r['state'] == 'ACTIVATED' for r in meta['methods'][m]['calibrated']) for m in METHODS})
+    print(out, os.path.getsize(out), 'bytes;', {m: sum(r['state'] == 'ACTIVATED' for r in meta['methods'][m]['calibrated']) for m in methods})
+
+
+def main():
+    ppq = refppq.load()
+    assert ppq is not None and refppq.root() == '/root/reference', 'generate fixtures from the read-only reference checkout'
+    from ppq.core import PPQ_CONFIG
+    assert PPQ_CONFIG.USING_CUDA_KERNEL is False
+    torch.set_num_threads(1)                                   # deterministic reductions
+    for net, methods in NETS.items(): generate(ppq, net, methods)
 
 
 if __name__ == '__main__':

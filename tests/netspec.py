@@ -26,8 +26,22 @@ TINY_RES = [
     dict(op='Flatten', name='flat', inputs=['gap.o'], out='flat.o'),
     dict(op='Gemm', name='fc', inputs=['flat.o'], out='y', cout=10, cin=24),
 ]
-SPECS = {'tinyres': TINY_RES}
-INPUT_SHAPE = {'tinyres': (3, 32, 32)}
+# TinyCat: two branches joined by a Concat ('Align to Output' by default, api/setting.py:254), a conv -> Sigmoid activation fusion, an AveragePool
+# (quantable, not passive, alignment 'None'), a max-pool whose producer has two consumers.
+TINY_CAT = [
+    dict(op='Conv', name='stem', inputs=['x'], out='stem.o', cout=8, cin=3, k=3, pad=1, stride=2, group=1),
+    dict(op='Relu', name='act0', inputs=['stem.o'], out='act0.o'),
+    dict(op='Conv', name='branch_a', inputs=['act0.o'], out='branch_a.o', cout=8, cin=8, k=3, pad=1, stride=1, group=1),
+    dict(op='Sigmoid', name='sig_a', inputs=['branch_a.o'], out='sig_a.o'),
+    dict(op='MaxPool', name='pool_b', inputs=['act0.o'], out='pool_b.o', k=3, stride=1, pad=1),
+    dict(op='Concat', name='cat', inputs=['sig_a.o', 'pool_b.o'], out='cat.o'),
+    dict(op='Conv', name='mix', inputs=['cat.o'], out='mix.o', cout=12, cin=16, k=1, pad=0, stride=1, group=1),
+    dict(op='Relu', name='act1', inputs=['mix.o'], out='act1.o'),
+    dict(op='AveragePool', name='avg', inputs=['act1.o'], out='avg.o', k=2, stride=2),
+    dict(op='Conv', name='head', inputs=['avg.o'], out='head.o', cout=6, cin=12, k=1, pad=0, stride=1, group=1),
+]
+SPECS = {'tinyres': TINY_RES, 'tinycat': TINY_CAT}
+INPUT_SHAPE = {'tinyres': (3, 32, 32), 'tinycat': (3, 32, 32)}
 
 
 def make_params(spec, seed):
@@ -73,7 +87,14 @@ class SpecNet(torch.nn.Module):
             elif o['op'] == 'Relu':
                 m = torch.nn.ReLU()
             elif o['op'] == 'MaxPool':
-                m = torch.nn.MaxPool2d(o['k'], o['stride'])
+                m = torch.nn.MaxPool2d(o['k'], o['stride'], padding=o.get('pad', 0))
+            elif o['op'] == 'AveragePool':
+                m = torch.nn.AvgPool2d(o['k'], o['stride'])
+            elif o['op'] == 'Sigmoid':
+                m = torch.nn.Sigmoid()
+            elif o['op'] == 'Concat':
+                from ppq_b200.executor import Concat as QConcat
+                m = QConcat(dim=1)
             elif o['op'] == 'GlobalAveragePool':
                 m = torch.nn.AvgPool2d(o['k'])             # the reference runs F.avg_pool2d(x, kernel_size=x.size()[2:]) (executor/op/torch/default.py:770)
             elif o['op'] == 'Flatten':
@@ -116,7 +137,11 @@ def build_ppq_graph(ppq, spec, params):
             ins += [v(o['name'] + '.w', params[o['name'] + '.w']), v(o['name'] + '.b', params[o['name'] + '.b'])]
             attrs = {'alpha': 1.0, 'beta': 1.0, 'transB': 1}
         elif o['op'] == 'MaxPool':
+            attrs = {'kernel_shape': [o['k']] * 2, 'strides': [o['stride']] * 2, 'pads': [o.get('pad', 0)] * 4}
+        elif o['op'] == 'AveragePool':
             attrs = {'kernel_shape': [o['k']] * 2, 'strides': [o['stride']] * 2, 'pads': [0, 0, 0, 0]}
+        elif o['op'] == 'Concat':
+            attrs = {'axis': 1}
         elif o['op'] == 'Flatten':
             attrs = {'axis': 1}
         g.create_operation(o['op'], name=o['name'], inputs=ins, outputs=[v(o['out'])], attributes=attrs)

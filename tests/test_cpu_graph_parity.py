@@ -17,11 +17,17 @@ import refppq
 from conftest import load_golden
 
 
+FIXTURES = {'tinyres': 'graph_pipeline.npz', 'tinycat': 'graph_pipeline_tinycat.npz'}
+
+
+def load_fixture(net):
+    z = load_golden(FIXTURES[net])
+    return z, json.loads(bytes(z['meta']).decode())
+
+
 @pytest.fixture(scope='module')
 def fx():
-    z = load_golden('graph_pipeline.npz')
-    meta = json.loads(bytes(z['meta']).decode())
-    return z, meta
+    return load_fixture('tinyres')
 
 
 def labels(spec):
@@ -45,10 +51,10 @@ def bits(a):
     return np.asarray(a, dtype=np.float32).reshape(-1).view(np.uint32)
 
 
-@pytest.mark.parametrize('method', ['kl', 'minmax', 'percentile', 'mse'])
-def test_cpu_pipeline_port_reproduces_the_reference_pipeline(fx, method):
+@pytest.mark.parametrize('net,method', [('tinyres', m) for m in ('kl', 'minmax', 'percentile', 'mse')] + [('tinycat', 'kl'), ('tinycat', 'percentile')])
+def test_cpu_pipeline_port_reproduces_the_reference_pipeline(net, method):
     from oracle.cpu_pipeline import CpuPipeline
-    z, meta = fx
+    z, meta = load_fixture(net)
     torch.set_num_threads(1)
     spec, params, data = net_and_data(meta)
     lab = labels(spec)
@@ -86,11 +92,12 @@ def test_cpu_pipeline_port_reproduces_the_reference_pipeline(fx, method):
     assert np.array_equal(bits(out), bits(z[f'{method}.output'])), np.abs(out - z[f'{method}.output']).max()
 
 
-def test_executor_topology_matches_the_reference_passes(fx):
+@pytest.mark.parametrize('net', ['tinyres', 'tinycat'])
+def test_executor_topology_matches_the_reference_passes(net):
     """QuantizeFusionPass + QuantizeSimplifyPass as mirrored by ppq_b200.executor: same OVERLAPPED configs, same group roots, same observed
     tensors in the same order as the reference graph (no GPU needed: tracing runs the fp32 modules on the CPU)."""
     from ppq_b200.executor import TorchExecutor
-    _, meta = fx
+    _, meta = load_fixture(net)
     spec, params, data = net_and_data(meta)
     lab = labels(spec)
     ex = TorchExecutor(netspec.SpecNet(spec, params), data[0], fuse_bn=False)

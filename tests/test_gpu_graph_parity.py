@@ -24,8 +24,7 @@ pytestmark = pytest.mark.gpu
 METHODS = ['kl', 'minmax', 'percentile', 'mse']
 
 
-@pytest.fixture(scope='module')
-def env():
+def make_env(fixture):
     if not torch.cuda.is_available(): pytest.skip('no CUDA device')
     ppq = refppq.load()
     if ppq is None: pytest.skip('reference package not present (pip install --target baseline/_ref, DESIGN.md §10)')
@@ -33,13 +32,24 @@ def env():
     torch.backends.cudnn.deterministic = True
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    z = load_golden('graph_pipeline.npz')
+    z = load_golden(fixture)
     meta = json.loads(bytes(z['meta']).decode())
     spec = netspec.SPECS[meta['net']]
     params = netspec.make_params(spec, meta['param_seed'])
     data = netspec.make_data(meta['net'], meta['data_seed'], meta['steps'], meta['batch'])
     from ppq_b200.ffi import extension
     return dict(ppq=ppq, z=z, meta=meta, spec=spec, params=params, data=data, ours=extension(), cache={})
+
+
+@pytest.fixture(scope='module')
+def env():
+    return make_env('graph_pipeline.npz')
+
+
+@pytest.fixture(scope='module')
+def env_cat():
+    """The second graph: Concat ('Align to Output'), conv -> Sigmoid fusion, AveragePool, a max-pool whose producer has two consumers."""
+    return make_env('graph_pipeline_tinycat.npz')
 
 
 def bits(a):
@@ -231,3 +241,20 @@ def test_graphwise_error_analyse_equals_the_reference_function(env):
         assert abs(got[k + '#0'] - v) <= 1e-6 + 2e-4 * abs(v), (k, got[k + '#0'], v)
     full = graphwise_error_analyse(ex, batches)                            # whole tensors, every operation: same order of magnitude, all below the 0.1 bar
     assert len(full) == len(ex.quantable_operations()) and all(0 <= e < 0.1 for e in full.values())
+
+
+@pytest.mark.parametrize('method', ['kl', 'percentile'])
+def test_second_graph_concat_alignment_and_sigmoid_fusion(env_cat, method):
+    """A + C on the Concat graph: the reference pipeline is identical under both native extensions, and our executor (arena flow, then Concat
+    'Align to Output' + baking) reproduces its configs, baked weights and quantised output bit for bit."""
+    from ppq_b200.executor import calibrate_arena
+    env = env_cat
+    assert_same(reference_run(env, 'ref', method), reference_run(env, 'ours', method), f'tinycat ref-ext vs ours [{method}]')
+    want = reference_run(env, 'ours', method)
+    ex, batches = our_executor(env)
+    calibrate_arena(ex, batches, method=method)
+    check_against(ex, env, want['calibrated'], f'tinycat/{method}/calibrated')
+    ex.align_quantization(); ex.bake_parameters()
+    check_against(ex, env, want['final'], f'tinycat/{method}/final')
+    out = ex.forward(batches[0]).cpu().numpy()
+    assert np.array_equal(bits(out), bits(want['output'])), np.abs(out - want['output']).max()
