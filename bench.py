@@ -18,7 +18,7 @@ fusion; synthetic randn / relu(randn) values) resident in HBM; `e2e` runs the re
 of the network with our hooks, scales read back -- through ppq_b200's public API.
 
 `--workload yolov5s` (BASELINE.json configs[4]) replays the activation set of the public YOLOv5s architecture at 3x640x640 (batch 16,
-512 samples per GPU = 4096 samples on 8 GPUs); replay only -- the network itself is not in the image.
+512 samples per GPU = 4096 samples on 8 GPUs); its e2e arm runs the architecture itself (bench_models.YOLOv5s, random init).
 
 Prints ONE JSON line (see the task contract): metric/value (imgs/s, whole job), roofline of the dominant kernel, cpu_baseline (the
 reference's USING_CUDA_KERNEL=False CPU path restated in oracle/ with torch CPU ops, timed on this host), clocks, e2e, gpu_launches,
@@ -122,7 +122,7 @@ WORKLOADS = {
     'resnet50': dict(table=resnet50_tensor_table, batch=32, image=(3, 224, 224),
                      name='ResNet-50 RuntimeCalibrationPass (minmax + KL 4096-bin histogram), 512 synthetic 3x224x224 samples per GPU'),
     'yolov5s': dict(table=yolov5s_tensor_table, batch=16, image=(3, 640, 640),
-                    name='YOLOv5s RuntimeCalibrationPass (minmax + KL 4096-bin histogram), 512 synthetic 3x640x640 samples per GPU (activation-set replay)'),
+                    name='YOLOv5s RuntimeCalibrationPass (minmax + KL 4096-bin histogram), 512 synthetic 3x640x640 samples per GPU'),
 }
 
 
@@ -355,7 +355,7 @@ def run_ours(args, rank, world, local_rank):
                      for r, v in enumerate(per_rank)],
     }
     cal.exchange_events = None
-    have_model = args.workload == 'resnet50'
+    have_model = True
     if rank == 0:
         result['fakequant'] = fakequant_sweep(ext, device, peak) if not args.no_sweep else None
     if not args.no_e2e and have_model:
@@ -436,8 +436,11 @@ def run_e2e(args, device, world, rank):
         from ppq_b200.executor import e2e_calibration_benchmark
     except Exception as e:                                               # executor lands after the kernels; never silently fake a number
         return {'value': None, 'unit': UNIT, 'unavailable': f'{type(e).__name__}: {e}'}
+    import bench_models
     return e2e_calibration_benchmark(batch=args.batch, batches=max(1, SAMPLES_PER_GPU // args.batch), steps=args.e2e_steps,
-                                     warmup=args.warmup, device=device, world=world, seed=rank, channels_last=args.e2e_channels_last)
+                                     warmup=args.warmup, device=device, world=world, seed=rank, channels_last=args.e2e_channels_last,
+                                     model=bench_models.build(args.workload), image=WORKLOADS[args.workload]['image'],
+                                     distinct_host_batches=16 if args.workload == 'resnet50' else 4)
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port of the reference CPU path)
@@ -525,14 +528,15 @@ def run_reference(args, rank, world):
     rate, info = cpu_replay_rate(args, budget_s=budget * 0.4, max_batches=args.steps)
     acts, weights = WORKLOADS[args.workload]['table']()
     e2e, e2e_info = None, None
-    if args.workload == 'resnet50':
-        import torchvision
+    if True:
+        import bench_models
         from oracle.cpu_pipeline import CpuPipeline
         torch.manual_seed(0)
-        pipe = CpuPipeline(torchvision.models.resnet50(weights=None), torch.zeros(1, 3, 224, 224))
+        image = WORKLOADS[args.workload]['image']
+        pipe = CpuPipeline(bench_models.build(args.workload), torch.zeros((1,) + image))
         pipe.quantize_parameters()
         g = torch.Generator().manual_seed(1)
-        x = torch.rand(args.batch, 3, 224, 224, generator=g)
+        x = torch.rand((args.batch,) + image, generator=g)
         times, t_search = [], None
         t_begin = time.perf_counter()
         for k in range(args.steps + 1):
@@ -558,7 +562,7 @@ def run_reference(args, rank, world):
                                        f"{len(acts)} activation tensors); {info['timed_batches']} step(s) timed + one KL search ({info['kl_search_s']} s) amortised over "
                                        f"{nb} batches; {info['seconds']} s on {info['threads']} threads"},
             'e2e': {'value': None if e2e is None else round(e2e, 2), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
-                    'what': 'CPU end-to-end pipeline incl. the torch CPU forward (oracle/cpu_pipeline.py), same batch as the GPU arm'}}
+                    'what': 'CPU end-to-end pipeline incl. the torch CPU forward (oracle/cpu_pipeline.py), same network and batch as the GPU arm'}}
 
 
 def main():

@@ -34,7 +34,7 @@ ELEMENTWISE = {'Add', 'Sub', 'Sum'}
 def _kind(m):
     table = {torch.nn.Conv2d: 'Conv', torch.nn.Linear: 'Gemm', torch.nn.ReLU: 'Relu', torch.nn.ReLU6: 'Clip', torch.nn.MaxPool2d: 'MaxPool',
              torch.nn.AdaptiveAvgPool2d: 'GlobalAveragePool', torch.nn.AvgPool2d: 'AveragePool', torch.nn.Flatten: 'Flatten',
-             torch.nn.Sigmoid: 'Sigmoid'}
+             torch.nn.Sigmoid: 'Sigmoid', torch.nn.SiLU: 'Swish', torch.nn.Upsample: 'Resize'}
     for t in type(m).__mro__:
         if t in table: return table[t]
         if t.__name__ in ('Add', 'Concat') and t.__module__ != 'torch.nn.modules.module': return t.__name__      # element-wise ops written as modules
@@ -246,7 +246,7 @@ class CpuPipeline:
                 master.parent, master.state = master, 'PASSIVE'
                 master._scale, master._offset = torch.tensor(s, dtype=torch.float32), torch.tensor(float(o), dtype=torch.float32)
                 for c in op.ins[1:]: c.slave_of(master)
-            elif op.kind == 'Concat':                                                          # 'Align to Output' (refine.py:484-496)
+            elif op.kind in ('Concat', 'Resize'):                                              # 'Align to Output' (refine.py:484-496)
                 master = op.out
                 for c in op.ins: c.slave_of(master)
             else:

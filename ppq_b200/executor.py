@@ -55,7 +55,10 @@ class Concat(torch.nn.Module):
 _KINDS = {torch.nn.Conv2d: 'Conv', torch.nn.ConvTranspose2d: 'ConvTranspose', torch.nn.Linear: 'Gemm', torch.nn.ReLU: 'Relu',
           torch.nn.ReLU6: 'Clip', torch.nn.MaxPool2d: 'MaxPool', torch.nn.AdaptiveAvgPool2d: 'GlobalAveragePool',
           torch.nn.AvgPool2d: 'AveragePool', torch.nn.Flatten: 'Flatten', torch.nn.Sigmoid: 'Sigmoid', torch.nn.GELU: 'Gelu',
-          torch.nn.Hardswish: 'HardSwish', torch.nn.Softmax: 'Softmax', torch.nn.LeakyReLU: 'LeakyRelu', Add: 'Add', Concat: 'Concat'}
+          torch.nn.Hardswish: 'HardSwish', torch.nn.Softmax: 'Softmax', torch.nn.LeakyReLU: 'LeakyRelu', Add: 'Add', Concat: 'Concat',
+          # x * sigmoid(x) as ONE module: fuses with its convolution exactly like the Conv - Sigmoid - Mul pattern upstream (refine.py:210-239),
+          # where only the Mul's output keeps a live config
+          torch.nn.SiLU: 'Swish', torch.nn.Upsample: 'Resize'}
 
 
 def kind_of(module: torch.nn.Module) -> Optional[str]:
@@ -71,7 +74,7 @@ PASSIVE_OPERATIONS = {'MaxPool', 'GlobalMaxPool', 'Reshape', 'Flatten', 'Identit
                       'Interp', 'Squeeze', 'Unsqueeze'}
 ACTIVATION_FUSION_TYPES = {'Relu', 'Clip', 'Swish', 'SoftPlus', 'Sigmoid', 'Gelu'}     # TensorRTQuantizer.py:103-104
 ELEMENTWISE_ALIGNMENT_TYPES = {'Add', 'Sub', 'Sum'}                                     # core/common.py:60-63
-CONCAT_ALIGNMENT_TYPES = {'Concat'}
+OUTPUT_ALIGNMENT_TYPES = {'Concat', 'Resize'}                                           # align_concat_to / align_resize_to: "Align to Output" 
 
 
 def fuse_conv_bn(model: torch.nn.Module) -> torch.nn.Module:
@@ -354,7 +357,7 @@ class TorchExecutor:
         """QuantAlignmentPass with the default setting (optim/refine.py:443-546; api/setting.py:251-256: element-wise 'Align to Large', concat
         'Align to Output', pooling 'None', force_alignment_overlap = True).
         Element-wise (Add / Sub / Sum): the first input config becomes the PASSIVE master of the op's inputs with the scale of the widest input
-        range.  Concat: the output config is the master, every input config is slaved to it.  With force_overlap (or a single consumer) the
+        range.  Concat / Resize: the output config is the master, every input config is slaved to it.  With force_overlap (or a single consumer) the
         producers' output configs are slaved to the master as well, so the tensors are quantised once, with the shared scale, where they are
         produced."""
         from .core import QuantizationProperty as P
@@ -380,7 +383,7 @@ class TorchExecutor:
                 master.scale, master.offset = scale.squeeze(0), offset.squeeze(0)
                 for slave in op.input_cfgs[1:]:
                     slave.master_by = master
-            elif op.kind in CONCAT_ALIGNMENT_TYPES:                                            # align_to_output (refine.py:484-496)
+            elif op.kind in OUTPUT_ALIGNMENT_TYPES:                                            # align_to_output (refine.py:484-496)
                 master = op.output_cfg
                 for slave in op.input_cfgs:
                     if slave.policy.has_property(P.FLOATING) or slave.state == QuantizationStates.FP32: continue
@@ -627,21 +630,25 @@ def graphwise_error_analyse(executor: TorchExecutor, batches, to_device=None, gr
 
 
 def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int, device, world: int = 1, seed: int = 0, graphs: bool = False,
-                              channels_last: bool = False):
-    """bench.py's `e2e`: ResNet-50 (random init, BN folded) calibrated end to end through the public API -- `batches` x `batch` images in pinned
-    host memory (this rank's share of the calibration set), H2D copy of every batch inside the timed region (both phases), torch forward with
-    per-forward weight fake-quant, multi-tensor collectors, the two all-reduces, on-device KL search and a D2H read of the resulting scales.
-    One step = one whole calibration; `steps` of them are timed after warm-up calibrations at the timed shape have converged (two consecutive
-    ones within 5 %: cuDNN autotuning, allocator growth, descriptor caches and clocks all settle there, not in a 2-batch dry run)."""
+                              channels_last: bool = False, model: torch.nn.Module = None, image=(3, 224, 224), distinct_host_batches: int = 16):
+    """bench.py's `e2e`: a network (default: torchvision ResNet-50; random init, BN folded) calibrated end to end through the public API -- `batches`
+    x `batch` images in pinned host memory (this rank's share of the calibration set), H2D copy of every batch inside the timed region (both
+    phases), torch forward with per-forward weight fake-quant, multi-tensor collectors, the two all-reduces, on-device KL search and a D2H read of
+    the resulting scales.  One step = one whole calibration; `steps` of them are timed after warm-up calibrations at the timed shape have
+    converged (two consecutive ones within 5 %: cuDNN autotuning, allocator growth, descriptor caches and clocks all settle there, not in a
+    2-batch dry run)."""
     import torch.distributed as dist
-    import torchvision
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
-    model = torchvision.models.resnet50(weights=None).eval()
-    ex = TorchExecutor(model.to(device), torch.zeros(2, 3, 224, 224, device=device), channels_last=channels_last)
+    if model is None:
+        import torchvision
+        model = torchvision.models.resnet50(weights=None)
+    model = model.eval()
+    ex = TorchExecutor(model.to(device), torch.zeros((2,) + tuple(image), device=device), channels_last=channels_last)
     ex.quantize_parameters()
     g = torch.Generator().manual_seed(1000 + seed)                         # every rank calibrates its OWN shard of the sample set
-    host = [torch.rand(batch, 3, 224, 224, generator=g).pin_memory() for _ in range(batches)]
+    distinct = [torch.rand((batch,) + tuple(image), generator=g).pin_memory() for _ in range(min(batches, distinct_host_batches))]
+    host = [distinct[k % len(distinct)] for k in range(batches)]            # big inputs (3x640x640): a few pinned batches cycled; every batch is still copied
     stream = torch.cuda.current_stream()
     act_cfgs = ex.observed_configs()
     to_dev = lambda x: x.to(device, non_blocking=True)                     # noqa: E731
@@ -699,7 +706,7 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
     step_ms = [a.elapsed_time(b) for a, b in per_step]
     total = ms / steps
     return {'value': round(world * steps * batches * batch / (ms * 1e-3), 1), 'unit': 'imgs/s',
-            'h2d_bytes_per_step': 2 * batches * batch * 3 * 224 * 224 * 4, 'd2h_bytes_per_step': int(scales.numel() * 4),
+            'h2d_bytes_per_step': 2 * batches * int(host[0].numel()) * 4, 'd2h_bytes_per_step': int(scales.numel() * 4),
             'ms_per_step': round(total, 3), 'steps': steps, 'step': f'one whole calibration: {batches} batches x {batch} images, both phases',
             'step_ms': {'min': round(min(step_ms), 3), 'median': round(sorted(step_ms)[len(step_ms) // 2], 3), 'max': round(max(step_ms), 3)},
             'warmup_calibrations_ms': [round(w, 2) for w in warm],

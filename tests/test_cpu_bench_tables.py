@@ -26,3 +26,26 @@ def test_reference_and_gpu_arm_share_one_config():
     acts, weights = bench.resnet50_tensor_table()
     cfg = bench.workload_config(args, acts, weights, 16)
     assert cfg['batch'] == 32 and cfg['samples_per_gpu_per_step'] == 512 and cfg['observed_tensors'] == 106
+
+
+def test_yolov5s_module_table_executor_and_cpu_port_agree():
+    """bench_models.YOLOv5s (the e2e arm), bench.yolov5s_tensor_table() (the replay arm), ppq_b200.executor's observed set and the CPU port's observed
+    set describe the same network: same 60 convolution weights, same 83 observed tensors."""
+    import torch
+
+    import bench
+    import bench_models
+    from oracle.cpu_pipeline import CpuPipeline
+    from ppq_b200.executor import TorchExecutor
+    net = bench_models.YOLOv5s()
+    acts, weights = bench.yolov5s_tensor_table()
+    assert sorted(tuple(c.weight.shape) for c in net.modules() if isinstance(c, torch.nn.Conv2d)) == sorted(weights)
+    ex = TorchExecutor(bench_models.YOLOv5s(), torch.zeros(1, 3, 64, 64))
+    kinds = [op.kind for _, op in ex.quantable_operations()]
+    assert kinds.count('Conv') == 60 and kinds.count('Swish') == 57 and kinds.count('Concat') == 13 and kinds.count('Add') == 7 and kinds.count('Resize') == 2
+    assert len(ex.observed_configs()) == len(acts) == 83
+    ops = dict(ex.quantable_operations())
+    assert ops['b0.conv#0'].output_cfg.dominated_by is ops['b0.act#0'].output_cfg          # Conv -> SiLU fusion (Conv - Sigmoid - Mul upstream)
+    assert ops['b9.m2#0'].output_cfg.dominated_by is ops['b9.cv1.act#0'].output_cfg        # SPPF max-pools are passive: they share the conv's config
+    port = CpuPipeline(bench_models.YOLOv5s(), torch.zeros(1, 3, 64, 64))
+    assert len(port.observed()) == 83
