@@ -228,3 +228,42 @@ def test_channels_last_network_is_read_in_storage_order(ext, oracle):
         return calibrate_arena(ex, data, method='minmax').scale, len(ex.observed_configs_all())
     (a, na), (b, nb) = scales(False), scales(True)
     assert na == nb and torch.allclose(a, b, rtol=2e-3, atol=1e-7), (a - b).abs().max()
+
+
+def test_config5_yolov5s_network_through_the_executor(ext):
+    """BASELINE config 5's network itself (bench_models.YOLOv5s: Conv-SiLU fusion, shortcut Adds, Concats, Upsamples, SPPF max-pools) at a small
+    resolution: the hook-driven pass and the arena calibrator (one multi-tensor launch per forward) give identical scales for all 83 observed tensors,
+    alignment makes every Add / Concat / Upsample input share its master's scale, and the quantised forward stays within the reference's SNR bar."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench_models
+    from ppq_b200.calibration import RuntimeCalibrationPass
+    from ppq_b200.core import QuantizationStates as S
+    from ppq_b200.executor import TorchExecutor, calibrate_arena, graphwise_error_analyse
+    torch.manual_seed(5)
+    data = [torch.rand(2, 3, 160, 160, device='cuda') for _ in range(8)]
+
+    def build():
+        torch.manual_seed(13)
+        ex = TorchExecutor(bench_models.YOLOv5s().cuda(), torch.zeros(1, 3, 160, 160, device='cuda'))
+        ex.quantize_parameters()
+        return ex
+    ex1 = build()
+    assert len(ex1.observed_configs()) == 83
+    RuntimeCalibrationPass(method='kl').optimize(graph=ex1, dataloader=data, executor=ex1, calib_steps=8)
+    s1 = torch.stack([c.scale for c in ex1.observed_configs_all()])
+    ex2 = build()
+    cal = calibrate_arena(ex2, data, method='kl')
+    assert torch.equal(cal.scale, s1)
+    ex3 = build()
+    cal3 = calibrate_arena(ex3, data, method='percentile')                 # the reference's default observer, one select table per forward
+    ex4 = build()
+    RuntimeCalibrationPass(method='percentile').optimize(graph=ex4, dataloader=data, executor=ex4, calib_steps=8)
+    assert torch.equal(cal3.scale, torch.stack([c.scale for c in ex4.observed_configs_all()]))
+    ex2.align_quantization()
+    for name, op in ex2.quantable_operations():
+        if op.kind in ('Add', 'Concat', 'Resize'):
+            master = op.input_cfgs[0].dominated_by
+            assert all(c.state == S.PASSIVE or c is master for c in op.input_cfgs) and all(c.scale is master.scale for c in op.input_cfgs), name
+    report = graphwise_error_analyse(ex2, data[:2])
+    assert all(0 <= v < 0.1 for v in report.values()), max(report.values())
