@@ -124,6 +124,17 @@ class DescriptorStager:
         return hit
 
 
+_STAGERS: Dict[tuple, DescriptorStager] = {}
+
+
+def shared_stager(device, columns: int) -> DescriptorStager:
+    """One stager per (device, table width) for the whole process: its pinned buffers are allocated once (cudaHostAlloc / cudaFreeHost synchronise
+    the device -- a calibrator that made its own ring paid that on every calibration)."""
+    key = (str(torch.device(device)), columns)
+    if key not in _STAGERS: _STAGERS[key] = DescriptorStager(device, columns)
+    return _STAGERS[key]
+
+
 class ArenaCalibrator:
     """method:  'minmax'      one phase: fused min/max                       -> MinMax_To_Scale_Offset
                 'kl'          + phase 2: 4096-bin histogram                  -> KL_Search
@@ -148,7 +159,7 @@ class ArenaCalibrator:
         self.hist = torch.zeros(num_tensors, bins if two_phase else 1, dtype=torch.int32, device=self.device)
         self.hist_scale = torch.zeros(num_tensors, dtype=torch.float32, device=self.device)
         self.scale = self.offset = self.best_bin_range = None
-        self._stager = DescriptorStager(self.device, 3, rows=max(num_tensors, 16))
+        self._stager = shared_stager(self.device, 3)
         self._pct: List[torch.Tensor] = []                               # per batch: [T, 2] {upper, lower} quantiles
         self._select_ws = None
         # per-slot thresholds remembered from the previous batch: consecutive batches of one activation are selected in ONE pass over the tensor

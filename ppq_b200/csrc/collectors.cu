@@ -263,8 +263,9 @@ __device__ __forceinline__ void hist_stream(const float *__restrict__ x, int64_t
     }
 }
 
-constexpr int kHistThreads = 1024;   // one big CTA per SM: the flush of the private bins (bins global atomics per CTA) is what
-                                     // limits small-CTA configurations (measured: 256 thr x 8/SM 59 % -> 1024 thr x 1/SM 82 % of HBM peak)
+constexpr int kHistThreads = 1024;   // big CTAs: the flush of the private bins (bins global atomics per CTA) is what limits small-CTA
+                                     // configurations (measured: 256 thr x 8/SM 59 % -> 1024 thr x 1/SM 82-86 % -> 1024 thr x 2/SM, two
+                                     // loads in flight, 87 % of HBM peak: r02_kbench.txt)
 template <int VARIANT, class Bin, int U = kUnroll, int TPB = kHistThreads, int MINB = 1>
 __global__ void __launch_bounds__(TPB, MINB)
 histogram_kernel(const float *__restrict__ x, int64_t n, BinParams bp, int32_t *__restrict__ hist) {
@@ -308,14 +309,14 @@ histogram_cluster_kernel(const float *__restrict__ x, int64_t n, BinParams bp, i
 
 // hist_scale read from device memory (phase 2 without a host round trip)
 template <int VARIANT>
-__global__ void __launch_bounds__(kHistThreads)
+__global__ void __launch_bounds__(kHistThreads, 2)
 histogram_dscale_kernel(const float *__restrict__ x, int64_t n, const float *__restrict__ hist_scale, int clip, int bins,
                         int32_t *__restrict__ hist) {
     extern __shared__ int sh[];
     hist_zero<VARIANT>(sh, bins);
     Counter<VARIANT> cnt(sh, hist, bins);
     const SymBin bin(__ldg(hist_scale), bins, clip != 0);
-    hist_stream<VARIANT>(x, n, (int64_t)blockIdx.x * kHistThreads + threadIdx.x, (int64_t)gridDim.x * kHistThreads, bin, cnt);
+    hist_stream<VARIANT, SymBin, 2>(x, n, (int64_t)blockIdx.x * kHistThreads + threadIdx.x, (int64_t)gridDim.x * kHistThreads, bin, cnt);
     hist_flush<VARIANT>(sh, bins, hist);
 }
 
@@ -403,14 +404,15 @@ static int launch_hist(const float *x, int64_t n, const BinParams &bin, int64_t 
     case 3:  histogram_kernel<3, Bin, kUnroll, kThreads><<<grid, kThreads, smem, st>>>(x, n, bin, hist); break;
     case 4:  histogram_kernel<0, Bin, 8, kThreads><<<grid * 8 > sm_count() * 8 ? sm_count() * 8 : grid * 8, kThreads, smem, st>>>(x, n, bin, hist); break;   // the round-1 small-CTA layout
     // 5 / 6: two 1024-thread CTAs per SM (32 registers per thread), 2 / 4 loads in flight per thread
-    case 5:  histogram_kernel<0, Bin, 2, kHistThreads, 2><<<grid * 2 > sm_count() * 2 ? sm_count() * 2 : grid * 2, kHistThreads, smem, st>>>(x, n, bin, hist); break;
+    case 5:  histogram_kernel<0, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;          // the round-1 default: one 1024-thread CTA per SM, 4 loads in flight
     case 6:  histogram_kernel<0, Bin, 4, kHistThreads, 2><<<grid * 2 > sm_count() * 2 ? sm_count() * 2 : grid * 2, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     // 7 / 8: thread-block clusters of 2 / 4 CTAs, DSMEM pre-reduction of the private bins (grid rounded down to whole clusters)
     case 7:  if (grid >= 2) { histogram_cluster_kernel<Bin, 2><<<grid & ~1, kHistThreads, smem, st>>>(x, n, bin, hist); break; }
              histogram_kernel<0, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     case 8:  if (grid >= 4) { histogram_cluster_kernel<Bin, 4><<<grid & ~3, kHistThreads, smem, st>>>(x, n, bin, hist); break; }
              histogram_kernel<0, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
-    default: histogram_kernel<0, Bin><<<grid, kHistThreads, smem, st>>>(x, n, bin, hist); break;
+    // default: two 1024-thread CTAs per SM (32 registers per thread), 2 loads in flight per thread
+    default: histogram_kernel<0, Bin, 2, kHistThreads, 2><<<grid * 2 > sm_count() * 2 ? sm_count() * 2 : grid * 2, kHistThreads, smem, st>>>(x, n, bin, hist); break;
     }
     return (int)cudaGetLastError();
 }
@@ -461,7 +463,7 @@ int ppq_b200_histogram_asym_t(const float *x, int64_t n, float vmin, float vmax,
 int ppq_b200_histogram_t_dscale(const float *x, int64_t n, const float *hist_scale_dev, int clip_outliers, int32_t *hist,
                                 int64_t bins, void *stream) {
     if (n <= 0 || !x || !hist || !hist_scale_dev || bins <= 0 || bins > kMaxSmemBins) return (int)cudaErrorInvalidValue;
-    const int grid = hist_grid(n, (int)bins);
+    const int grid = hist_grid(n, (int)bins) * 2 > sm_count() * 2 ? sm_count() * 2 : hist_grid(n, (int)bins) * 2;
     histogram_dscale_kernel<0><<<grid, kHistThreads, (size_t)(bins + 1) * sizeof(int), (cudaStream_t)stream>>>(
         x, n, hist_scale_dev, clip_outliers, (int)bins, hist);
     return (int)cudaGetLastError();

@@ -23,7 +23,7 @@
 //            rank asks for it).
 // Algorithmic traffic: 4 B/element; this design moves 8 B/element (two streaming passes), the round-1 version 12.
 // No allocation -- the caller provides the workspace.  The result is the identical element, bit for bit, except that a selected zero is
-// always reported as +0.0 (equal as a float to whichever zero the reference's sort left at that index).
+// reported with the sign its key order gives (-0.0 < +0.0), equal as a float to whichever zero the reference's sort left at that index.
 #include "common.cuh"
 #include "../../include/ppq_b200.h"
 
@@ -63,12 +63,13 @@ __host__ __device__ constexpr int level_shift(int level) { return level == 0 ? 2
 __host__ __device__ constexpr uint32_t level_dmask(int level) { return level == 2 ? 0x3FFu : 0x7FFu; }
 __host__ __device__ constexpr uint32_t level_pmask(int level) { return level == 0 ? 0u : (level == 1 ? 0xFFE00000u : 0xFFFFFC00u); }
 
+// Order-preserving key: flip all bits of negative floats, only the sign bit of the others (an arithmetic shift + one LOP3 -- pass 0 is bound by
+// the integer pipe, every instruction per element counts).  Total order: -NaN < -inf < ... < -0.0 < +0.0 < ... < +inf < +NaN.  thrust's radix
+// sort treats -0.0 and +0.0 as one key; here -0.0 sorts just below +0.0, so a selected zero may carry either sign -- equal as a float to whichever
+// zero the reference's stable sort left at that index (the sign is not recoverable without sorting).
 __device__ __forceinline__ uint32_t order_key(float v) {
-    uint32_t b = __float_as_uint(v);
-    if (b == 0x80000000u) b = 0u;          // -0.0 and +0.0 are one key, as in CUB's radix sort (which thrust::sort dispatches to);
-                                           // the selected zero is reported as +0.0 (the reference reports whichever zero its stable
-                                           // sort left at that index -- equal as floats, the sign is not recoverable without a sort)
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    const uint32_t b = __float_as_uint(v);
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
 }
 __device__ __forceinline__ float key_to_float(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
@@ -266,12 +267,10 @@ __device__ __forceinline__ bool select_pass(const float *__restrict__ x, int64_t
         if (need1 && hi == p1) take(k, 1, m1, a1, buf1, kmin1, kmax1);
     };
     // Fast rejection on the RAW bits (levels 1-2): key & pmask == p  <=>  bits & pmask == raw(p), because the key transform only depends on
-    // the sign, which the prefix fixes.  -0.0 is the one exception (its key is +0's): when a prefix is the bucket of +0 the raw pattern of
-    // -0.0 is accepted too; a false positive only costs the exact test in count().  One AND + three compares per element.
-    auto raw_of = [&](uint32_t p) { return (p & 0x80000000u) ? (p & 0x7FFFFFFFu) : (~p & pmask); };
-    const uint32_t zero_bucket = 0x80000000u & pmask;                   // the bucket of +0 at this level
-    const uint32_t c0 = raw_of(p0), c1 = raw_of(p1), c2 = (p0 == zero_bucket || p1 == zero_bucket) ? 0x80000000u : c0;
-    auto hit = [&](float f) { const uint32_t t = __float_as_uint(f) & pmask; return (t == c0) | (t == c1) | (t == c2); };
+    // the sign, which the prefix fixes.  One AND + two compares per element.
+    auto raw_of = [&](uint32_t p) { return (p & 0x80000000u) ? (p & 0x7FFFFFFFu & pmask) : (~p & pmask); };
+    const uint32_t c0 = raw_of(p0), c1 = raw_of(p1);
+    auto hit = [&](float f) { const uint32_t t = __float_as_uint(f) & pmask; return (t == c0) | (t == c1); };
     auto visit4 = [&](const float4 &v) {
         if (LEVEL != 0 && !(hit(v.x) | hit(v.y) | hit(v.z) | hit(v.w))) return;
         count(order_key(v.x)); count(order_key(v.y)); count(order_key(v.z)); count(order_key(v.w));
@@ -526,7 +525,9 @@ static int select_two(const float *x, int64_t n, int q_mode, float q, long long 
         select_pass0_spec_kernel<<<g0 > sm_count() ? sm_count() : g0, kSelThreads, 0, s>>>(x, n, st, bufs, cap);
     } else select_pass_kernel<0, kSelThreads><<<grid_pass0(n), kSelThreads, 0, s>>>(x, n, st, bufs, cap);
     select_pass_kernel<1, kFilterThreads><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
-    select_pass_kernel<2, kFilterThreads><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
+    // pass 2 is rarely needed (a bucket too big to compact that holds several distinct values): two CTAs per SM keep its usual early exit cheap
+    const int g2 = grid_filter(n) > 2 * sm_count() ? 2 * sm_count() : grid_filter(n);
+    select_pass_kernel<2, kFilterThreads><<<g2, kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
     select_finish_kernel<<<2, kSelThreads, 0, s>>>(st, bufs, cap, nullptr, out, 0, guess);
     return (int)cudaGetLastError();
 }
@@ -583,7 +584,7 @@ int ppq_b200_multi_quantile_t(const ppq_b200_tensor_desc *descs, int count, int6
     select_scan_kernel<0><<<count, kSelThreads, 0, s>>>(states, cap);
     multi_select_pass_kernel<1, kFilterThreads><<<g1, kFilterThreads, smem, s>>>(descs, count, states, bufs, cap);
     select_scan_kernel<1><<<count, kSelThreads, 0, s>>>(states, cap);
-    multi_select_pass_kernel<2, kFilterThreads><<<g1, kFilterThreads, smem, s>>>(descs, count, states, bufs, cap);
+    multi_select_pass_kernel<2, kFilterThreads><<<g1 > 2 * sm_count() ? 2 * sm_count() : g1, kFilterThreads, smem, s>>>(descs, count, states, bufs, cap);
     select_scan_kernel<2><<<count, kSelThreads, 0, s>>>(states, cap);
     select_finish_kernel<<<2 * count, kSelThreads, 0, s>>>(states, bufs, cap, descs, out, out_stride, guess);
     return (int)cudaGetLastError();

@@ -42,6 +42,13 @@ void *Stream() { return (void *)at::cuda::getCurrentCUDAStream().stream(); }
 // Per-TENSOR operators are order-independent (element-wise maps, reductions, histograms, order statistics): any dense layout (e.g. a
 // channels_last activation) is processed in storage order, without the NCHW copy `.contiguous()` would make; at::empty_like keeps the strides.
 Tensor Dense(const Tensor &t) { return t.is_non_overlapping_and_dense() ? t : t.contiguous(); }
+// Operators that RETURN a tensor keep the reference's layout contract (output = empty_like of the contiguous value, linear.cu:106-112) except for
+// the channels_last memory formats, where -- like torch's own element-wise operators -- the format is preserved instead of copying to NCHW.
+Tensor DenseFormat(const Tensor &t) {
+    if (t.is_contiguous()) return t;
+    if ((t.dim() == 4 && t.is_contiguous(at::MemoryFormat::ChannelsLast)) || (t.dim() == 5 && t.is_contiguous(at::MemoryFormat::ChannelsLast3d))) return t;
+    return t.contiguous();
+}
 const float *F(const Tensor &t) { return t.data_ptr<float>(); }
 
 struct Geometry { int64_t epc; int C; };
@@ -66,7 +73,7 @@ Tensor QuantizeTensor_LT(const Tensor &value, const Tensor &scale, const Tensor 
     CheckTensor(offset, at::kFloat, "Offset(Expect to be FP32)");
     CheckSize(value);
     const c10::cuda::CUDAGuard guard(value.device());
-    auto v = Dense(value);
+    auto v = DenseFormat(value);
     Tensor out = at::empty_like(v);
     CheckStatus(ppq_b200_linear_quant_t(F(v), out.data_ptr<float>(), v.numel(), F(scale), F(offset), clip_min, clip_max, rounding,
                                         Stream()), "QuantizeTensor_LT");
@@ -121,7 +128,7 @@ Tensor QuantizeTensor_FT(const Tensor &value, const Tensor &scale, const Tensor 
     CheckTensor(scale, at::kFloat, "Scale(Expect to be FP32)");
     CheckTensor(offset, at::kFloat, "Offset(Expect to be FP32)");
     const c10::cuda::CUDAGuard guard(value.device());
-    auto v = Dense(value);
+    auto v = DenseFormat(value);
     Tensor out = at::empty_like(v);
     CheckStatus(ppq_b200_float_quant_t(F(v), out.data_ptr<float>(), v.numel(), F(scale), F(offset), exponent, mantissa, clip_min,
                                        clip_max, rounding, Stream()), "QuantizeTensor_FT");
