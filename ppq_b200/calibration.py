@@ -204,7 +204,7 @@ class ArenaCalibrator:
             if self._select_ws is None or self._select_ws.numel() < need:
                 self._select_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             self.ext.Multi_Quantile_T(descs, max_n, self.percentile, self._batch_quantiles(), 2, self._select_ws, self.select_cap, self._select_guess)
-            self.launches += 8
+            self.launches += 5
             return
         if self.phase == 1:
             self.ext.Multi_MinMax_T(descs, max_n, self.minmax)

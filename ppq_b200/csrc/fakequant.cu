@@ -186,13 +186,18 @@ template <class Op, class OutT, bool VEC4>
 __global__ void __launch_bounds__(kThreads)
 ew_channel_table_kernel(const float *__restrict__ x, OutT *__restrict__ y, uint32_t n, uint32_t epc, int C, FastDiv32 div_epc, FastDiv32 div_C,
                         const float *__restrict__ scale, const float *__restrict__ offset, typename Op::Params p) {
-    __shared__ float4 tab[kTabRows];
+    // Two tables: tile t builds into tab[t & 1] and needs ONE barrier (after the build).  Every warp passes the barrier of tile t + 1 only after its
+    // own apply stage of tile t, so when a table is rebuilt (tile t + 2) nobody reads it any more -- and a warp that runs ahead has already issued
+    // the loads of the next tile when it waits at that barrier, so the memory pipe of the CTA never drains at a tile boundary.
+    __shared__ float4 tab[2][kTabRows];
     const typename Op::Plan plan(p);
     const float4 *x4 = reinterpret_cast<const float4 *>(x);
     const uint32_t groups = (n + 3u) >> 2;                              // VEC4: n % 4 == 0
     const uint32_t n4 = n >> 2;                                         // whole vectors
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t base = blockIdx.x * (uint32_t)kTileVec; base < groups; base += gridDim.x * (uint32_t)kTileVec) {
+    uint32_t which = 0;
+    for (uint32_t base = blockIdx.x * (uint32_t)kTileVec; base < groups; base += gridDim.x * (uint32_t)kTileVec, which ^= 1u) {
+        float4 *t = tab[which];
         const uint32_t v0 = base + warp * (32 * kUnroll) + lane;
         float4 v[kUnroll];
 #pragma unroll
@@ -202,7 +207,7 @@ ew_channel_table_kernel(const float *__restrict__ x, OutT *__restrict__ y, uint3
         const uint32_t r0 = div_epc.quot(e_first), rows = div_epc.quot(e_last) - r0 + 1u;
         for (uint32_t i = threadIdx.x; i < rows; i += kThreads) {
             const uint32_t row = r0 + i, c = row - div_C.quot(row) * (uint32_t)C;
-            tab[i] = Op::entry(__ldg(scale + c), __ldg(offset + c));
+            t[i] = Op::entry(__ldg(scale + c), __ldg(offset + c));
         }
         __syncthreads();
 #pragma unroll
@@ -212,30 +217,28 @@ ew_channel_table_kernel(const float *__restrict__ x, OutT *__restrict__ y, uint3
             const uint32_t e0 = vi << 2;
             const uint32_t row = div_epc.quot(e0);
             if constexpr (VEC4) {
-                const Op op(plan, tab[row - r0]);
+                const Op op(plan, t[row - r0]);
                 Emit<Op, OutT>::vec(op, v[j], y, (int64_t)vi);
             } else {
                 uint32_t col = e0 - row * epc, idx = row - r0;
+                Op op(plan, t[idx]);                                    // re-read the table only when the walk crosses a row end
                 if (vi < n4) {
                     const float in[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
                     OutT out[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const Op op(plan, tab[idx]);
                         out[k] = Emit<Op, OutT>::one(op, in[k]);
-                        if (++col == epc) { col = 0; ++idx; }
+                        if (++col == epc) { col = 0; ++idx; if (k < 3) op.rebind(t[idx]); }
                     }
                     Emit<Op, OutT>::store4(y, vi, out[0], out[1], out[2], out[3]);
                 } else {                                                // the <= 3 elements after the last whole vector
                     for (uint32_t e = e0; e < n; e++) {
-                        const Op op(plan, tab[idx]);
                         y[e] = Emit<Op, OutT>::one(op, ld_stream1(x + e));
-                        if (++col == epc) { col = 0; ++idx; }
+                        if (++col == epc) { col = 0; ++idx; if (e + 1 < n) op.rebind(t[idx]); }
                     }
                 }
             }
         }
-        __syncthreads();                                                // the next tile rebuilds the table
     }
 }
 
@@ -509,7 +512,7 @@ static int launch_channel(const float *x, OutT *y, int64_t n, int64_t epc, int C
     const bool al = aligned16(x) && out_aligned<OutT>(y);
     const auto table_grid = [&]() {
         int64_t tiles = ((n + 3) / 4 + kTileVec - 1) / kTileVec;
-        const int64_t cap = (int64_t)sm_count() * 6;                    // 40+ registers, 16.6 KB of table: six CTAs per SM
+        const int64_t cap = (int64_t)sm_count() * 5;                    // 44 registers, 2 x 16.4 KB of tables: five CTAs per SM
         return (int)(tiles < cap ? tiles : cap);
     };
     if (epc % 4 == 0 && al) {

@@ -36,6 +36,7 @@ struct LinearOp {
         return make_float4(e.s, e.r, __int_as_float(offset_to_int(off)), 0.f);
     }
     __device__ __forceinline__ LinearOp(const Plan &p, const float4 &e) : lo(p.lo), hi(p.hi), mode(p.mode) { d.s = e.x; d.r = e.y; o = __float_as_int(e.z); }
+    __device__ __forceinline__ void rebind(const float4 &e) { d.s = e.x; d.r = e.y; o = __float_as_int(e.z); }
     __device__ __forceinline__ int finish(float t) const {
         int q;
         if constexpr (MODE >= 0) q = round2int<MODE>(t); else q = round2int_dyn(t, mode);
@@ -100,6 +101,7 @@ struct FloatOp {
     __device__ __forceinline__ void rebind(float s, float o) { d.init(s); off = o; }
     static __device__ __forceinline__ float4 entry(float s, float o) { ExactDiv e(s); return make_float4(e.s, e.r, o, 0.f); }
     __device__ __forceinline__ FloatOp(const Plan &p, const float4 &e) : pl(p), off(e.z) { d.s = e.x; d.r = e.y; }
+    __device__ __forceinline__ void rebind(const float4 &e) { d.s = e.x; d.r = e.y; off = e.z; }
     static constexpr float kDivLimit = 1.15e18f;                                        // ~2^60: beyond this use div.rn
     // u = x / s already computed exactly; returns the value on the FP(E,M) grid
     __device__ __forceinline__ float grid(float u) const {

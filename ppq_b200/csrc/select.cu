@@ -129,7 +129,7 @@ __device__ __forceinline__ void block_pick(Load &&load, unsigned long long k, un
     __syncthreads();
 }
 
-// Resolve a pass for one tensor: run by the last CTA of the pass (single tensor) or by select_scan_kernel (tables).
+// Resolve a pass for one tensor: run by the last CTA to finish its part of that tensor (ticket counter), in both the single-tensor and the table form.
 template <int LEVEL, int TPB>
 __device__ __noinline__ void select_scan(SelectState *st, long long cap) {
     __shared__ unsigned int s_digit;
@@ -231,6 +231,16 @@ __device__ __forceinline__ void stream_range(const float *__restrict__ x, int64_
     }
 }
 
+// Does this tensor need a streaming pass at LEVEL?  (uniform over the grid: it only reads what the previous scan wrote)
+template <int LEVEL>
+__device__ __forceinline__ bool level_needed(const SelectState *st) {
+    if (LEVEL == 0) return true;
+    const unsigned m0 = st->mode[0], m1 = st->mode[1];
+    const bool need0 = m0 == kModeHist || (m0 == kModeCompact && !st->compacted[0]);
+    const bool need1 = !st->shared && (m1 == kModeHist || (m1 == kModeCompact && !st->compacted[1]));
+    return need0 || need1;
+}
+
 // One pass over the part [a, b) of a tensor for the CTA (`first`, `stride` in threads of the cooperating group).  Returns false when the
 // tensor needs nothing at this level (uniform over the grid).
 template <int LEVEL, int TPB>
@@ -302,6 +312,8 @@ __device__ __forceinline__ bool select_pass(const float *__restrict__ x, int64_t
     return true;
 }
 
+template <int TPB> __device__ __forceinline__ void finish_tensor_pass(SelectState *st, unsigned expected, bool *is_last);
+
 // Pass 0 with speculation (table form, `guess` given): the digit histogram of every element as in select_pass<0>, and on the way every key
 // beyond the thresholds remembered from the previous call of this slot (the previous batch of the same activation: the tail moves little
 // from batch to batch) is compacted -- except copies of the previously selected key, which are only counted.  When the candidates turn out
@@ -368,6 +380,7 @@ multi_select_pass0_spec_kernel(const ppq_b200_tensor_desc *__restrict__ descs, i
                                uint32_t *__restrict__ bufs, int64_t cap) {
     __shared__ int sh[2][kDigits];
     __shared__ unsigned int sh_cnt[2];
+    __shared__ bool is_last;
     extern __shared__ long long prefix[];                              // [count + 1]
     if (threadIdx.x == 0) {
         long long run = 0;
@@ -384,12 +397,16 @@ multi_select_pass0_spec_kernel(const ppq_b200_tensor_desc *__restrict__ descs, i
     { int lo = 0, hi = count - 1; while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (prefix[mid] <= s0) lo = mid; else hi = mid - 1; } t = lo; }
     for (; t < count && prefix[t] < s1; t++) {
         const ppq_b200_tensor_desc d = descs[t];
+        if (d.n <= 0) continue;
         int64_t a = s0 - prefix[t]; if (a < 0) a = 0;
         int64_t b = s1 - prefix[t]; if (b > d.n) b = d.n;
         a = (a + 3) & ~(int64_t)3; if (a > d.n) a = d.n;
         if (b < d.n) b = (b + 3) & ~(int64_t)3; if (b > d.n) b = d.n;
-        if (b <= a) continue;
-        select_pass0_spec<kSelThreads>(d.x, a, b, threadIdx.x, kSelThreads, states + t, bufs + (int64_t)t * 2 * cap, cap, sh, sh_cnt);
+        SelectState *st = states + t;
+        if (b > a) select_pass0_spec<kSelThreads>(d.x, a, b, threadIdx.x, kSelThreads, st, bufs + (int64_t)t * 2 * cap, cap, sh, sh_cnt);
+        const unsigned expected = (unsigned)((prefix[t + 1] - 1) / span - prefix[t] / span + 1);
+        finish_tensor_pass<kSelThreads>(st, expected, &is_last);
+        if (is_last) { __threadfence(); select_scan<0, kSelThreads>(st, cap); }
         __syncthreads();
     }
 }
@@ -413,13 +430,23 @@ select_pass_kernel(const float *__restrict__ x, int64_t n, SelectState *__restri
     }
 }
 
-// ---- tables: each CTA owns one contiguous span of the concatenation of all tensors; a separate one-CTA-per-tensor launch resolves the pass
+// ---- tables: each CTA owns one contiguous span of the concatenation of all tensors.  The CTAs that overlap a tensor are known from the span
+// arithmetic alone, so the last of them to finish resolves that tensor's pass (ticket counter), as in the single-tensor kernel: no extra launch.
+template <int TPB>
+__device__ __forceinline__ void finish_tensor_pass(SelectState *st, unsigned expected, bool *is_last) {
+    __threadfence();                                                   // this CTA's atomics are ordered before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) *is_last = (atomicAdd(&st->done, 1u) == expected - 1u);
+    __syncthreads();
+}
+
 template <int LEVEL, int TPB>
 __global__ void __launch_bounds__(TPB, LEVEL == 0 ? 2 : 6)
 multi_select_pass_kernel(const ppq_b200_tensor_desc *__restrict__ descs, int count, SelectState *__restrict__ states,
                          uint32_t *__restrict__ bufs, int64_t cap) {
     __shared__ int sh[2][kDigits];
     __shared__ unsigned int sh_cnt[2];
+    __shared__ bool is_last;
     extern __shared__ long long prefix[];                              // [count + 1]
     if (threadIdx.x == 0) {
         long long run = 0;
@@ -436,27 +463,22 @@ multi_select_pass_kernel(const ppq_b200_tensor_desc *__restrict__ descs, int cou
     { int lo = 0, hi = count - 1; while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (prefix[mid] <= s0) lo = mid; else hi = mid - 1; } t = lo; }
     for (; t < count && prefix[t] < s1; t++) {
         const ppq_b200_tensor_desc d = descs[t];
+        if (d.n <= 0) continue;
         int64_t a = s0 - prefix[t]; if (a < 0) a = 0;
         int64_t b = s1 - prefix[t]; if (b > d.n) b = d.n;
         a = (a + 3) & ~(int64_t)3; if (a > d.n) a = d.n;               // both neighbours round the shared boundary the same way
         if (b < d.n) b = (b + 3) & ~(int64_t)3; if (b > d.n) b = d.n;
-        if (b <= a) continue;                                          // uniform per CTA
-        select_pass<LEVEL, TPB>(d.x, a, b, threadIdx.x, TPB, states + t, bufs + (int64_t)t * 2 * cap, cap, sh, sh_cnt);
+        SelectState *st = states + t;
+        bool active;                                                   // uniform over the grid
+        if (b > a) active = select_pass<LEVEL, TPB>(d.x, a, b, threadIdx.x, TPB, st, bufs + (int64_t)t * 2 * cap, cap, sh, sh_cnt);
+        else active = level_needed<LEVEL>(st);                         // overlaps the tensor by less than a vector: no data, but a ticket
+        if (active) {
+            const unsigned expected = (unsigned)((prefix[t + 1] - 1) / span - prefix[t] / span + 1);
+            finish_tensor_pass<TPB>(st, expected, &is_last);
+            if (is_last) { __threadfence(); select_scan<LEVEL, TPB>(st, cap); }
+        }
         __syncthreads();
     }
-}
-
-template <int LEVEL>
-__global__ void __launch_bounds__(kSelThreads)
-select_scan_kernel(SelectState *states, int64_t cap) {
-    SelectState *st = states + blockIdx.x;
-    if (LEVEL > 0) {                                                   // nothing was streamed for this tensor at this level
-        const unsigned m0 = st->mode[0], m1 = st->mode[1];
-        const bool need0 = m0 == kModeHist || (m0 == kModeCompact && !st->compacted[0]);
-        const bool need1 = !st->shared && (m1 == kModeHist || (m1 == kModeCompact && !st->compacted[1]));
-        if (!need0 && !need1) return;
-    }
-    select_scan<LEVEL, kSelThreads>(st, cap);
 }
 
 // ---- finish: one CTA per (tensor, rank) selects among the compacted keys (or just reports a resolved key) -------------------------------
@@ -581,11 +603,8 @@ int ppq_b200_multi_quantile_t(const ppq_b200_tensor_desc *descs, int count, int6
         const int gs = g0 > sm_count() ? sm_count() : g0;
         multi_select_pass0_spec_kernel<<<gs, kSelThreads, smem, s>>>(descs, count, states, bufs, cap);
     } else multi_select_pass_kernel<0, kSelThreads><<<g0, kSelThreads, smem, s>>>(descs, count, states, bufs, cap);
-    select_scan_kernel<0><<<count, kSelThreads, 0, s>>>(states, cap);
     multi_select_pass_kernel<1, kFilterThreads><<<g1, kFilterThreads, smem, s>>>(descs, count, states, bufs, cap);
-    select_scan_kernel<1><<<count, kSelThreads, 0, s>>>(states, cap);
     multi_select_pass_kernel<2, kFilterThreads><<<g1 > 2 * sm_count() ? 2 * sm_count() : g1, kFilterThreads, smem, s>>>(descs, count, states, bufs, cap);
-    select_scan_kernel<2><<<count, kSelThreads, 0, s>>>(states, cap);
     select_finish_kernel<<<2 * count, kSelThreads, 0, s>>>(states, bufs, cap, descs, out, out_stride, guess);
     return (int)cudaGetLastError();
 }
