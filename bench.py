@@ -323,7 +323,7 @@ def run_ours(args, rank, world, local_rank):
     mm_gbs = 4.0 * wl.act_elems / (m_ms * 1e-3) / 1e9
     traffic = None
     try:                                                                    # dram__bytes_read + dram__bytes_write of one launch, from the committed ncu capture
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
         if tj.get('batch') == args.batch and args.workload == 'resnet50': traffic = tj['traffic_bytes_per_launch']
     except Exception:
         pass

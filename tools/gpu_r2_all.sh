@@ -21,7 +21,7 @@ echo "== bench ours"; timeout 900 python bench.py --steps 20 --warmup 5 > gpurun
 echo "== bench e2e NHWC A/B"; timeout 400 python bench.py --steps 3 --warmup 3 --no-sweep --no-cpu-baseline --e2e-channels-last > gpurun_out/r2_bench_e2e_nhwc.json 2> gpurun_out/r2_bench_e2e_nhwc.err; echo "nhwc exit $?"; python -c "
 import json; d=json.loads(open('gpurun_out/r2_bench_e2e_nhwc.json').read().strip().split(chr(10))[-1]); print(json.dumps(d['e2e']))" 2>&1 | cut -c1-1500; tail -3 gpurun_out/r2_bench_e2e_nhwc.err
 echo "== bench yolov5s"; timeout 600 python bench.py --workload yolov5s --steps 10 --warmup 3 --no-sweep > gpurun_out/r2_bench_yolo_n1.json 2> gpurun_out/r2_bench_yolo.err; echo "yolo exit $?"; cut -c1-3500 gpurun_out/r2_bench_yolo_n1.json; tail -3 gpurun_out/r2_bench_yolo.err
-echo "== ncu launch list"; ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches.csv timeout 600 python bench.py --steps 1 --warmup 3 --no-e2e --no-sweep --no-cpu-baseline > gpurun_out/r2_bench_under_ncu.log 2>&1; wc -l gpurun_out/r2_launches.csv
+echo "== ncu launch list"; ncu --nvtx --nvtx-include "timed/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches.csv timeout 600 python bench.py --steps 1 --warmup 3 --no-e2e --no-sweep --no-cpu-baseline > gpurun_out/r2_bench_under_ncu.log 2>&1; wc -l gpurun_out/r2_launches.csv
 echo "== ncu captures"
 ncu --set full --clock-control none --import-source on -k regex:select_pass -s 8 -c 3 -f -o gpurun_out/r2_prof_select timeout 300 python tools/kbench.py --only quantile --reps 1 > gpurun_out/r2_ncu_select.log 2>&1; tail -1 gpurun_out/r2_ncu_select.log
 ncu --set full --clock-control none --import-source on -k regex:multi_select_pass0_spec -s 3 -c 1 -f -o gpurun_out/r2_prof_select_spec timeout 300 python tools/kbench.py --only quantile --reps 1 > gpurun_out/r2_ncu_select_spec.log 2>&1; tail -1 gpurun_out/r2_ncu_select_spec.log

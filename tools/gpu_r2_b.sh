@@ -12,3 +12,6 @@ echo "== bench yolov5s"; timeout 900 python bench.py --workload yolov5s --steps 
 import json; d=json.loads(open('gpurun_out/r2b_bench_yolo_n1.json').read().strip().split(chr(10))[-1]); print('value', d['value'], 'e2e', json.dumps(d['e2e']), 'cpu', json.dumps(d['cpu_baseline'])[:300])" 2>&1 | cut -c1-2500; tail -3 gpurun_out/r2b_bench_yolo.err
 echo "== yolov5s reference arm"; timeout 500 python bench.py --impl reference --workload yolov5s --steps 6 --warmup 1 --ref-budget 120 > gpurun_out/r2b_bench_yolo_ref.json 2> gpurun_out/r2b_bench_yolo_ref.err; echo "exit $?"; cut -c1-300 gpurun_out/r2b_bench_yolo_ref.json; python -c "
 import json; d=json.loads(open('gpurun_out/r2b_bench_yolo_ref.json').read().strip().split(chr(10))[-1]); print('value', d['value'], 'e2e', d['e2e']['value'], json.dumps(d['arm'])[:600])"
+echo "== ncu launch list (timed NVTX range only)"; ncu --nvtx --nvtx-include "timed/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches.csv timeout 600 python bench.py --steps 1 --warmup 3 --no-e2e --no-sweep --no-cpu-baseline > gpurun_out/r2_bench_under_ncu.log 2>&1; wc -l gpurun_out/r2_launches.csv
+ncu --set full --clock-control none --import-source on -k regex:select_pass -s 8 -c 3 -f -o gpurun_out/r2_prof_select timeout 300 python tools/kbench.py --only quantile --reps 1 > gpurun_out/r2_ncu_select.log 2>&1; tail -1 gpurun_out/r2_ncu_select.log
+ncu --set full --clock-control none --import-source on -k regex:ew_channel_table -s 2 -c 2 -f -o gpurun_out/r2_prof_lc_table timeout 300 python tools/kbench.py --only lc --reps 1 > gpurun_out/r2_ncu_lc.log 2>&1; tail -1 gpurun_out/r2_ncu_lc.log
