@@ -230,10 +230,8 @@ kl_search_warp_kernel(const int32_t *__restrict__ hist_arena, int bins, const fl
     double *pre = reinterpret_cast<double *>(kl_smem + (((size_t)bins * 4 + 7) & ~(size_t)7));      // [bins + 1]
     double *logp = pre + pre_len;                                     // [bins]
     double *loss = logp + bins;                                       // [ncand]
-    double *glogq_all = loss + ((ncand + 1) & ~1);                    // [32 warps][quant_bins]
-    float *gval_all = reinterpret_cast<float *>(glogq_all + (size_t)(kKlwThreads / 32) * quant_bins);   // [32 warps][quant_bins]
+    float *gval_all = reinterpret_cast<float *>(loss + ((ncand + 1) & ~1));      // [32 warps][quant_bins]: a warp's per-group spread values
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double *glogq = glogq_all + (size_t)w * quant_bins;
     float *gval = gval_all + (size_t)w * quant_bins;
 
     const int32_t *hist = hist_arena + (int64_t)blockIdx.x * bins;
@@ -266,37 +264,37 @@ kl_search_warp_kernel(const int32_t *__restrict__ hist_arena, int bins, const fl
     __syncthreads();
 
     for (int c = w; c < ncand; c += kKlwThreads / 32) {
+        // candidate bin_range = (c + 1) * quant_bins: every group spans `ratio` = c + 1 bins.  A lane owns whole groups (lane, lane + 32, ...),
+        // so nothing in the loops divides an index by the ratio and a group's q and log10(q) stay in registers.
         const int br = (c + 1) * quant_bins, ratio = c + 1;
+        double qs = 0.0;
         for (int g = lane; g < quant_bins; g += 32) {
             const int a = g * ratio;
             int cnt = 0;
             for (int i = a; i < a + ratio; i++) cnt += h[i] > 0.f;
-            gval[g] = __fdiv_rn((float)(pre[a + ratio] - pre[a]), (float)(cnt == 0 ? 1 : cnt));
+            const float spread = __fdiv_rn((float)(pre[a + ratio] - pre[a]), (float)(cnt == 0 ? 1 : cnt));
+            gval[g] = spread;
+            qs += (double)spread * (double)cnt;                          // the sum over the group's non-empty bins of their spread value
         }
-        __syncwarp();
-        double qs = 0.0;
-        for (int i = lane; i < br; i += 32) if (h[i] > 0.f) qs += (double)gval[i / ratio];
         const float qsum = (float)warp_sum(qs);
         const float tail = (float)(pre[bins] - pre[br]);
-        const float q_empty = __fdiv_rn(0.f, qsum);
-        __syncwarp();
-        for (int g = lane; g < quant_bins; g += 32) {
-            const float q = __fdiv_rn(gval[g], qsum);
-            gval[g] = q;
-            glogq[g] = log10((double)q + 1e-30);
-        }
-        __syncwarp();
+        const float q_empty = __fdiv_rn(0.f, qsum);                      // 0/0 = NaN when every bin of the candidate is empty, as upstream
+        const double lq_empty = log10((double)q_empty + 1e-30);
         double kl = 0.0;
-        for (int i = lane; i < br; i += 32) {
-            float pv = h[i];
-            const bool nonempty = pv > 0.f, last = (i == br - 1);
-            if (last) pv = __fadd_rn(pv, tail);
-            const float p = __fdiv_rn(pv, total);
-            const float q = nonempty ? gval[i / ratio] : q_empty;
-            if (p == 0.f && q == q) continue;
-            const double lp = last ? log10((double)p + 1e-30) : logp[i];
-            const double lq = nonempty ? glogq[i / ratio] : log10((double)q + 1e-30);
-            kl += (double)p * (lp - lq);
+        for (int g = lane; g < quant_bins; g += 32) {
+            const int a = g * ratio;
+            const float q = __fdiv_rn(gval[g], qsum);
+            const double lq = log10((double)q + 1e-30);
+            for (int i = a; i < a + ratio; i++) {
+                float pv = h[i];
+                const bool nonempty = pv > 0.f, last = (i == br - 1);
+                if (last) pv = __fadd_rn(pv, tail);
+                const float p = __fdiv_rn(pv, total);
+                const float qq = nonempty ? q : q_empty;
+                if (p == 0.f && qq == qq) continue;                      // 0 * (finite) contributes exactly 0
+                const double lp = last ? log10((double)p + 1e-30) : logp[i];
+                kl += (double)p * (lp - (nonempty ? lq : lq_empty));
+            }
         }
         kl = warp_sum(kl);
         if (lane == 0) loss[c] = kl;
@@ -428,7 +426,7 @@ int ppq_b200_kl_search(const int32_t *hist_arena, int64_t count, int64_t bins, c
         const size_t ncand = (size_t)(bins / qb);
         const size_t plen = (size_t)(bins + 1 > kKlwThreads ? bins + 1 : kKlwThreads);
         const size_t smem_w = (((size_t)bins * 4 + 7) & ~(size_t)7) + plen * 8 + (size_t)bins * 8 + ((ncand + 1) & ~(size_t)1) * 8 +
-                              (size_t)(kKlwThreads / 32) * (size_t)qb * 12;
+                              (size_t)(kKlwThreads / 32) * (size_t)qb * 4;
         if (smem_w <= 220 * 1024) {
             if (smem_w > 48 * 1024 && cudaFuncSetAttribute(kl_search_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
                 return (int)cudaGetLastError();
