@@ -3,7 +3,7 @@
 # integer-pipe fixes, default bench (e2e with the persistent descriptor stager), NHWC A/B, yolov5s with its e2e arm.
 mkdir -p gpurun_out
 echo "== tests"; timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 2>&1 | grep -v "^  \|^$" | grep -v "^tests/.*\]$" | cut -c1-400 | tail -60 > gpurun_out/r2b_tests.log; tail -40 gpurun_out/r2b_tests.log
-echo "== kbench"; timeout 300 python tools/kbench.py --only hist,quantile,lc --reps 20 > gpurun_out/r2b_kbench.txt 2>&1; cat gpurun_out/r2b_kbench.txt
+echo "== kbench"; timeout 300 python tools/kbench.py --only hist,quantile,lc,kl --reps 20 > gpurun_out/r2b_kbench.txt 2>&1; cat gpurun_out/r2b_kbench.txt
 echo "== bench ours"; timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2b_bench_n1.json 2> gpurun_out/r2b_bench.err; echo "bench exit $?"; python -c "
 import json; d=json.loads(open('gpurun_out/r2b_bench_n1.json').read().strip().split(chr(10))[-1]); print('value', d['value'], 'e2e', json.dumps(d['e2e']), 'cpu', json.dumps(d['cpu_baseline'])[:300])" 2>&1 | cut -c1-2500; tail -5 gpurun_out/r2b_bench.err
 echo "== bench e2e NHWC A/B"; timeout 400 python bench.py --steps 3 --warmup 3 --no-sweep --no-cpu-baseline --e2e-channels-last > gpurun_out/r2b_bench_e2e_nhwc.json 2> gpurun_out/r2b_bench_e2e_nhwc.err; echo "nhwc exit $?"; python -c "
