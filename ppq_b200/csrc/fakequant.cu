@@ -221,17 +221,15 @@ ew_channel_table_kernel(const float *__restrict__ x, OutT *__restrict__ y, uint3
                 Emit<Op, OutT>::vec(op, v[j], y, (int64_t)vi);
             } else {
                 uint32_t col = e0 - row * epc, idx = row - r0;
-                Op op(plan, t[idx]);                                    // re-read the table only when the walk crosses a row end
                 if (vi < n4) {
-                    const float in[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-                    OutT out[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        out[k] = Emit<Op, OutT>::one(op, in[k]);
-                        if (++col == epc) { col = 0; ++idx; if (k < 3) op.rebind(t[idx]); }
-                    }
-                    Emit<Op, OutT>::store4(y, vi, out[0], out[1], out[2], out[3]);
+                    // epc >= 4: the four elements of a vector lie in at most two rows.  Both table entries are read, every lane picks its row with
+                    // a select, and the four quotients share one range test (the 4-operator form of the channel-last kernel) -- no branch per element.
+                    const uint32_t left = epc - col;                    // elements of the vector that still belong to row `idx` (>= 1)
+                    const float4 E0 = t[idx], E1 = t[min(idx + 1u, rows - 1u)];
+                    const Op ops[4] = {Op(plan, E0), Op(plan, left > 1u ? E0 : E1), Op(plan, left > 2u ? E0 : E1), Op(plan, left > 3u ? E0 : E1)};
+                    Emit<Op, OutT>::vecx(ops, v[j], y, (int64_t)vi);
                 } else {                                                // the <= 3 elements after the last whole vector
+                    Op op(plan, t[idx]);
                     for (uint32_t e = e0; e < n; e++) {
                         y[e] = Emit<Op, OutT>::one(op, ld_stream1(x + e));
                         if (++col == epc) { col = 0; ++idx; if (e + 1 < n) op.rebind(t[idx]); }
