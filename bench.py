@@ -565,7 +565,27 @@ def run_reference(args, rank, world):
                     'what': 'CPU end-to-end pipeline incl. the torch CPU forward (oracle/cpu_pipeline.py), same network and batch as the GPU arm'}}
 
 
+def host_cpu_quota():
+    """CPUs this process may actually use (cgroup quota / affinity), not the CPUs the host reports: the B200 boxes report 128 and grant 16, and
+    one OpenMP thread per *reported* CPU makes torch's host-side ops crawl (spinning threads under a CFS quota)."""
+    n = os.cpu_count() or 1
+    try: n = min(n, len(os.sched_getaffinity(0)))
+    except Exception: pass
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        if quota != 'max': n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read()); p_ = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0: n = min(n, max(1, q // p_))
+        except Exception: pass
+    return max(1, n)
+
+
 def main():
+    import faulthandler
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(240, repeat=True, file=sys.stderr)          # a stuck run leaves its stacks in stderr instead of nothing
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20, help='timed steps; one step = one whole calibration of 512 samples per GPU')
@@ -591,6 +611,7 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm')
+    if 'OMP_NUM_THREADS' not in os.environ: torch.set_num_threads(host_cpu_quota())   # torchrun sets it to 1 per rank; a bare `python bench.py` must not take 128
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
