@@ -471,7 +471,7 @@ def prefetch_to_device(batches, to_device, device):
 
 @torch.no_grad()
 def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=None, to_device=None, deferred='auto',
-                    graphs: bool = False, prefetch: bool = True):
+                    graphs: bool = False, prefetch: bool = True, trace: list = None):
     """Two-phase calibration of every observed activation through one ArenaCalibrator (statistics arena, one all-reduce per
     phase, on-device scale search).  `batches` is this rank's share of the calibration set (sample-sharded by the caller).
     deferred=False observes each tensor as the forward produces it (one launch per tensor);
@@ -491,10 +491,15 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
     cal = ArenaCalibrator(len(cfgs), dev, method=method, group=group)
     static_in = None
     mutated = None                                                        # slots whose tensors are overwritten later in the forward
+    phase = 0
     while True:
         graph = None
+        phase += 1
         overlapped = prefetch and to_device is not None and not graphs and dev.type == 'cuda'
-        for x in (prefetch_to_device(batches, to_device, dev) if overlapped else batches):
+        for index, x in enumerate(prefetch_to_device(batches, to_device, dev) if overlapped else batches):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True); ev.record(torch.cuda.current_stream(dev))
+                trace.append((phase, index, time.perf_counter(), ev))
             cal.begin_batch()
             if graphs:
                 if static_in is None:
@@ -541,7 +546,13 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
                     del tensors, rest
             else:
                 executor.forward(x, sink=cal.observe_one)
+        if trace is not None:
+            ev = torch.cuda.Event(enable_timing=True); ev.record(torch.cuda.current_stream(dev))
+            trace.append((phase, len(batches), time.perf_counter(), ev))
         if cal.end_phase(): break
+    if trace is not None:
+        ev = torch.cuda.Event(enable_timing=True); ev.record(torch.cuda.current_stream(dev))
+        trace.append((phase + 1, 0, time.perf_counter(), ev))
     for i, c in enumerate(cfgs):
         c.scale, c.offset, c.state = cal.scale[i], cal.offset[i], QuantizationStates.ACTIVATED
     return cal
@@ -656,8 +667,11 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
     def reset():
         for c in act_cfgs: c.state = QuantizationStates.INITIAL
 
+    traces = []
+
     def run():
-        cal = calibrate_arena(ex, host, method='kl', to_device=to_dev, graphs=graphs)
+        traces.append([])
+        cal = calibrate_arena(ex, host, method='kl', to_device=to_dev, graphs=graphs, trace=traces[-1])
         s = cal.scale.cpu()                                               # D2H of the result (synchronises)
         reset()
         return s
@@ -680,6 +694,7 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     per_step = []
+    del traces[:]
     t0.record(stream)
     for _ in range(steps):
         a = torch.cuda.Event(enable_timing=True); a.record(stream)
@@ -694,6 +709,7 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
     if world > 1:
         t = torch.tensor([ms], device=device); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
     assert bool(torch.isfinite(scales).all()) and bool((scales > 0).all())
+    timed_traces = traces[:steps]
 
     # ---- breakdown (untimed, after the measurement): where a calibration batch's time goes
     def forwards(bypass):
@@ -711,15 +727,24 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
         h2d = min(timed(lambda: [to_dev(x) for x in host for _ in range(2)])[0] for _ in range(2))
     nb2 = 2.0 * batches
     step_ms = [a.elapsed_time(b) for a, b in per_step]
+    # the slowest timed calibration, batch by batch: the largest gap between two consecutive batch marks on the host clock (time to ENQUEUE a
+    # batch: Python, hooks, launches, allocator) and on the device clock (time to EXECUTE it), and where it fell
+    slow = timed_traces[max(range(len(step_ms)), key=lambda i: step_ms[i])]
+    gaps = [(slow[i + 1][2] - slow[i][2]) * 1e3 for i in range(len(slow) - 1)]
+    dgaps = [slow[i][3].elapsed_time(slow[i + 1][3]) for i in range(len(slow) - 1)]
+    hi, di = max(range(len(gaps)), key=gaps.__getitem__), max(range(len(dgaps)), key=dgaps.__getitem__)
+    where = lambda i: f'phase {slow[i][0]} batch {slow[i][1]}' if slow[i][1] < batches else f'phase {slow[i][0]} end (exchange / search)'   # noqa: E731
+    slowest = {'ms': round(max(step_ms), 3), 'host_enqueue_gap_ms': {'median': round(sorted(gaps)[len(gaps) // 2], 3), 'max': round(gaps[hi], 3), 'at': where(hi)},
+               'device_gap_ms': {'median': round(sorted(dgaps)[len(dgaps) // 2], 3), 'max': round(dgaps[di], 3), 'at': where(di)}}
     total = ms / steps
     return {'value': round(world * steps * batches * batch / (ms * 1e-3), 1), 'unit': 'imgs/s',
             'h2d_bytes_per_step': 2 * batches * int(host[0].numel()) * 4, 'd2h_bytes_per_step': int(scales.numel() * 4),
             'ms_per_step': round(total, 3), 'steps': steps, 'step': f'one whole calibration: {batches} batches x {batch} images, both phases',
             'step_ms': {'min': round(min(step_ms), 3), 'median': round(sorted(step_ms)[len(step_ms) // 2], 3), 'max': round(max(step_ms), 3)},
-            'warmup_calibrations_ms': [round(w, 2) for w in warm],
+            'warmup_calibrations_ms': [round(w, 2) for w in warm], 'slowest_step': slowest,
             'observed_tensors': int(scales.numel()), 'cuda_graphs': graphs, 'channels_last': channels_last, 'python_gc': 'collected before, disabled inside the timed region',
             'breakdown_ms_per_batch_pass': {'forward_fp32_cudnn': round(pure / nb2, 3), 'hooks_and_weight_fakequant': round((hooked - pure) / nb2, 3),
                                             'collectors_exchange_search': round((total - hooked) / nb2, 3),
                                             'h2d_copy_overlapped': round(h2d / nb2, 3), 'total': round(total / nb2, 3)},
-            'what': 'pinned-host images -> H2D -> torch ResNet-50 forward (fp32, cuDNN) with per-forward INT8 per-channel weight fake-quant '
+            'what': f'pinned-host images -> H2D -> torch {type(ex.model).__name__} forward (fp32, cuDNN) with per-forward INT8 per-channel weight fake-quant '
                     '-> multi-tensor min/max (phase 1) / histogram (phase 2) -> all-reduce -> on-device KL search -> scales D2H'}
