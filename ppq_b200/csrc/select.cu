@@ -243,7 +243,7 @@ __device__ __forceinline__ bool level_needed(const SelectState *st) {
 
 // One pass over the part [a, b) of a tensor for the CTA (`first`, `stride` in threads of the cooperating group).  Returns false when the
 // tensor needs nothing at this level (uniform over the grid).
-template <int LEVEL, int TPB, int U = 4>
+template <int LEVEL, int TPB>
 __device__ __forceinline__ bool select_pass(const float *__restrict__ x, int64_t a, int64_t b, int64_t first, int64_t stride,
                                             SelectState *__restrict__ st, uint32_t *__restrict__ bufs, int64_t cap, int (*sh)[kDigits], unsigned int *sh_cnt) {
     constexpr int shift = level_shift(LEVEL);
@@ -286,7 +286,7 @@ __device__ __forceinline__ bool select_pass(const float *__restrict__ x, int64_t
         count(order_key(v.x)); count(order_key(v.y)); count(order_key(v.z)); count(order_key(v.w));
     };
     auto visit1 = [&](float f) { count(order_key(f)); };
-    stream_range<U, LEVEL != 0>(x, a, b, first, stride, visit4, visit1);
+    stream_range<4, LEVEL != 0>(x, a, b, first, stride, visit4, visit1);
     __syncthreads();
     // flush: histograms with global atomics on the non-empty digits, staged keys after one reservation per CTA and rank
     __shared__ unsigned int s_base[2];
@@ -412,15 +412,13 @@ multi_select_pass0_spec_kernel(const ppq_b200_tensor_desc *__restrict__ descs, i
 }
 
 // ---- single tensor: the whole grid interleaves over the tensor, the last CTA to finish resolves the pass ------------------------------
-// U = 128-bit loads in flight per thread: the filter passes do ~8 instructions per element and wait on memory (long_scoreboard 11 of 17 stall
-// cycles per issue at U = 4: profiles/r02_select.md), so big tensors take 8 (4 KB contiguous per warp), like the fake-quant kernels.
-template <int LEVEL, int TPB, int U = 4>
-__global__ void __launch_bounds__(TPB, LEVEL == 0 ? 2 : (U == 4 ? 6 : 4))
+template <int LEVEL, int TPB>
+__global__ void __launch_bounds__(TPB, LEVEL == 0 ? 2 : 6)
 select_pass_kernel(const float *__restrict__ x, int64_t n, SelectState *__restrict__ st, uint32_t *__restrict__ bufs, int64_t cap) {
     __shared__ int sh[2][kDigits];
     __shared__ unsigned int sh_cnt[2];
     __shared__ bool is_last;
-    if (!select_pass<LEVEL, TPB, U>(x, 0, n, (int64_t)blockIdx.x * TPB + threadIdx.x, (int64_t)gridDim.x * TPB, st, bufs, cap, sh, sh_cnt)) return;
+    if (!select_pass<LEVEL, TPB>(x, 0, n, (int64_t)blockIdx.x * TPB + threadIdx.x, (int64_t)gridDim.x * TPB, st, bufs, cap, sh, sh_cnt)) return;
     // every CTA's atomics are ordered before its ticket
     __threadfence();
     __syncthreads();
@@ -548,10 +546,7 @@ static int select_two(const float *x, int64_t n, int q_mode, float q, long long 
         const int g0 = grid_pass0(n);
         select_pass0_spec_kernel<<<g0 > sm_count() ? sm_count() : g0, kSelThreads, 0, s>>>(x, n, st, bufs, cap);
     } else select_pass_kernel<0, kSelThreads><<<grid_pass0(n), kSelThreads, 0, s>>>(x, n, st, bufs, cap);
-    if (n >= ((int64_t)1 << 25)) {
-        const int g1 = grid_filter(n) > 4 * sm_count() ? 4 * sm_count() : grid_filter(n);
-        select_pass_kernel<1, kFilterThreads, 8><<<g1, kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
-    } else select_pass_kernel<1, kFilterThreads><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
+    select_pass_kernel<1, kFilterThreads><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
     // pass 2 is rarely needed (a bucket too big to compact that holds several distinct values): two CTAs per SM keep its usual early exit cheap
     const int g2 = grid_filter(n) > 2 * sm_count() ? 2 * sm_count() : grid_filter(n);
     select_pass_kernel<2, kFilterThreads><<<g2, kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
