@@ -481,7 +481,10 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
     graphs=True captures one forward per phase -- network kernels, per-forward weight fake-quant and the collectors -- into a CUDA
     graph and replays it for every batch (fixed batch shape).  Measured on B200 (ResNet-50, 8 x 32 images): capture + instantiate
     costs more than it saves at 8-16 batches per phase (1330 vs 3124 imgs/s end to end), so it is off by default; it pays off for long
-    calibration sets or when the same graph is reused across calls."""
+    calibration sets or when the same graph is reused across calls.
+    trace: a list that receives (phase, batch index, host time, CUDA event) before every batch and at the end of a phase -- bench.py's e2e uses
+    it to say whether a slow calibration was slow on the host or on the device, and where."""
+    import time
     from .calibration import ArenaCalibrator, is_dense
     cfgs = executor.observed_configs()
     for c in cfgs: c.observer_algorithm = method

@@ -267,3 +267,21 @@ def test_config5_yolov5s_network_through_the_executor(ext):
             assert all(c.state == S.PASSIVE or c is master for c in op.input_cfgs) and all(c.scale is master.scale for c in op.input_cfgs), name
     report = graphwise_error_analyse(ex2, data[:2])                       # a random-init 25-layer-deep network: a sanity bound, not the 0.1 bar of trained ones
     assert len(report) == len(ex2.quantable_operations()) and all(0 <= v < 0.5 for v in report.values()), max(report.values())
+
+
+@pytest.mark.gpu
+def test_e2e_benchmark_arm_runs_and_reports_its_breakdown(ext):
+    """bench.py's `e2e` arm at toy size (host batches -> H2D -> hooked forward -> collectors -> search -> D2H): the function the driver's headline comes
+    from must run, count its bytes from the tensors it copies and attribute the slowest calibration to host or device (per-batch trace)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench_models
+    from ppq_b200.executor import e2e_calibration_benchmark
+    r = e2e_calibration_benchmark(batch=2, batches=3, steps=2, warmup=2, device=torch.device('cuda:0'), channels_last=True,
+                                  model=bench_models.YOLOv5s(), image=(3, 96, 96), distinct_host_batches=2)
+    assert r['value'] > 0 and r['observed_tensors'] == 83 and r['steps'] == 2
+    assert r['h2d_bytes_per_step'] == 2 * 3 * 2 * 3 * 96 * 96 * 4 and r['d2h_bytes_per_step'] == 83 * 4
+    slow = r['slowest_step']
+    assert slow['ms'] == r['step_ms']['max'] and slow['host_enqueue_gap_ms']['max'] >= slow['host_enqueue_gap_ms']['median'] > 0
+    assert slow['device_gap_ms']['at'].startswith('phase ')
+    assert set(r['breakdown_ms_per_batch_pass']) == {'forward_fp32_cudnn', 'hooks_and_weight_fakequant', 'collectors_exchange_search', 'h2d_copy_overlapped', 'total'}
