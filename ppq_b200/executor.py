@@ -445,11 +445,68 @@ def _min_scale_of(cfg) -> float:
 
 
 # ------------------------------------------------------------------------------------------------------------------ calibration drivers
+class DeviceBatchRing:
+    """Two persistent device buffers and one persistent copy stream per device for the calibration inputs: batch k+1 is copied host->device on the
+    copy stream into the slot batch k-1 has been consumed from, while batch k runs.  Nothing is allocated per batch and nothing crosses streams
+    inside the caching allocator (the first version allocated every batch on a fresh side stream and handed it over with `record_stream`)."""
+    _rings = {}
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [None, None]
+
+    @classmethod
+    def of(cls, device):
+        device = torch.device(device)
+        key = (device.type, torch.cuda.current_device() if device.index is None else device.index)
+        ring = cls._rings.get(key)
+        if ring is None: ring = cls._rings[key] = cls(device)
+        return ring
+
+    def put(self, slot: int, x: torch.Tensor):
+        buf = self.slots[slot]
+        if buf is None or buf.shape != x.shape or buf.dtype != x.dtype:
+            buf = self.slots[slot] = torch.empty(x.shape, dtype=x.dtype, device=self.device)   # allocated on the caller's stream, kept
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if self.consumed[slot] is not None: self.stream.wait_event(self.consumed[slot])
+        with torch.cuda.stream(self.stream):
+            buf.copy_(x, non_blocking=True)
+            self.ready[slot].record(self.stream)
+        return buf
+
+    def release(self, slot: int):
+        ev = self.consumed[slot]
+        if ev is None: ev = self.consumed[slot] = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+
+
 def prefetch_to_device(batches, to_device, device):
-    """Yield `to_device(batch)` for every batch with the copy of batch k+1 enqueued on a side stream before batch k is handed out, so
-    the host->device transfer of the next calibration batch (19 MB for 32 images) overlaps the forward of the current one."""
-    copy_stream = torch.cuda.Stream(device=device)
+    """Yield every batch on the device with the copy of batch k+1 enqueued on a side stream before batch k is handed out, so the host->device
+    transfer of the next calibration batch (19 MB for 32 images) overlaps the forward of the current one.
+    to_device='ring': the batches are host tensors (pinned for a truly asynchronous copy); they go through the device's DeviceBatchRing -- the
+    yielded tensor is valid until the next one is requested.  A callable to_device keeps the generic path (whatever it returns is allocated on a
+    side stream and handed to the consumer's stream)."""
     it = iter(batches)
+    if isinstance(to_device, str):
+        if to_device != 'ring': raise ValueError(f"to_device must be a callable or 'ring', got {to_device!r}")
+        ring = DeviceBatchRing.of(device)
+        main = torch.cuda.current_stream(device)
+        x = next(it, None)
+        ahead = None if x is None else ring.put(0, x)
+        k = 0
+        while ahead is not None:
+            y, slot = ahead, k % 2
+            main.wait_event(ring.ready[slot])
+            x = next(it, None)
+            ahead = None if x is None else ring.put((k + 1) % 2, x)
+            yield y
+            ring.release(slot)                                           # everything the consumer enqueued for batch k precedes this event
+            k += 1
+        return
+    copy_stream = DeviceBatchRing.of(device).stream
 
     def fetch():
         x = next(it, None)
@@ -482,8 +539,9 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
     graph and replays it for every batch (fixed batch shape).  Measured on B200 (ResNet-50, 8 x 32 images): capture + instantiate
     costs more than it saves at 8-16 batches per phase (1330 vs 3124 imgs/s end to end), so it is off by default; it pays off for long
     calibration sets or when the same graph is reused across calls.
-    trace: a list that receives (phase, batch index, host time, CUDA event) before every batch and at the end of a phase -- bench.py's e2e uses
-    it to say whether a slow calibration was slow on the host or on the device, and where."""
+    to_device: a callable applied to every batch, or 'ring' for host tensors staged through the device's persistent DeviceBatchRing.
+    trace: a list that receives (phase, batch index, host time, CUDA event, thread CPU time) before every batch and at the end of a phase --
+    bench.py's e2e uses it to say whether a slow calibration was slow on the host or on the device, and where."""
     import time
     from .calibration import ArenaCalibrator, is_dense
     cfgs = executor.observed_configs()
@@ -502,7 +560,7 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
         for index, x in enumerate(prefetch_to_device(batches, to_device, dev) if overlapped else batches):
             if trace is not None:
                 ev = torch.cuda.Event(enable_timing=True); ev.record(torch.cuda.current_stream(dev))
-                trace.append((phase, index, time.perf_counter(), ev))
+                trace.append((phase, index, time.perf_counter(), ev, time.thread_time()))
             cal.begin_batch()
             if graphs:
                 if static_in is None:
@@ -524,7 +582,7 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
                     cal.minmax.copy_(keep_mm); cal.hist.copy_(keep_h)      # capture does not execute, but stay safe
                 graph.replay()
                 continue
-            if to_device is not None and not overlapped: x = to_device(x)
+            if to_device is not None and not overlapped: x = x.to(dev, non_blocking=True) if isinstance(to_device, str) else to_device(x)
             if deferred is True:
                 _, tensors = executor.forward(x, collect=True)
                 cal.observe([t if is_dense(t) else t.contiguous() for t in tensors])
@@ -551,11 +609,11 @@ def calibrate_arena(executor: TorchExecutor, batches, method: str = 'kl', group=
                 executor.forward(x, sink=cal.observe_one)
         if trace is not None:
             ev = torch.cuda.Event(enable_timing=True); ev.record(torch.cuda.current_stream(dev))
-            trace.append((phase, len(batches), time.perf_counter(), ev))
+            trace.append((phase, len(batches), time.perf_counter(), ev, time.thread_time()))
         if cal.end_phase(): break
     if trace is not None:
         ev = torch.cuda.Event(enable_timing=True); ev.record(torch.cuda.current_stream(dev))
-        trace.append((phase + 1, 0, time.perf_counter(), ev))
+        trace.append((phase + 1, 0, time.perf_counter(), ev, time.thread_time()))
     for i, c in enumerate(cfgs):
         c.scale, c.offset, c.state = cal.scale[i], cal.offset[i], QuantizationStates.ACTIVATED
     return cal
@@ -665,7 +723,7 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
     host = [distinct[k % len(distinct)] for k in range(batches)]            # big inputs (3x640x640): a few pinned batches cycled; every batch is still copied
     stream = torch.cuda.current_stream()
     act_cfgs = ex.observed_configs()
-    to_dev = lambda x: x.to(device, non_blocking=True)                     # noqa: E731
+    to_dev = lambda x: x.to(device, non_blocking=True)                     # noqa: E731  (raw copy, for the breakdown's H2D line)
 
     def reset():
         for c in act_cfgs: c.state = QuantizationStates.INITIAL
@@ -674,7 +732,7 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
 
     def run():
         traces.append([])
-        cal = calibrate_arena(ex, host, method='kl', to_device=to_dev, graphs=graphs, trace=traces[-1])
+        cal = calibrate_arena(ex, host, method='kl', to_device='ring', graphs=graphs, trace=traces[-1])
         s = cal.scale.cpu()                                               # D2H of the result (synchronises)
         reset()
         return s
@@ -699,11 +757,16 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
     per_step = []
     del traces[:]
     t0.record(stream)
+    def alloc_counters():
+        m = torch.cuda.memory_stats(device)
+        return [m.get('num_device_alloc', 0), m.get('num_device_free', 0), m.get('num_alloc_retries', 0), m.get('reserved_bytes.all.current', 0)]
+
+    counters = [alloc_counters()]
     for _ in range(steps):
         a = torch.cuda.Event(enable_timing=True); a.record(stream)
         scales = run()
         b = torch.cuda.Event(enable_timing=True); b.record(stream)
-        per_step.append((a, b))
+        per_step.append((a, b)); counters.append(alloc_counters())
     t1.record(stream)
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
@@ -717,7 +780,7 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
     # ---- breakdown (untimed, after the measurement): where a calibration batch's time goes
     def forwards(bypass):
         for _ in range(2):                                                # two passes over the set, like the two phases
-            for x in prefetch_to_device(host, to_dev, device):
+            for x in prefetch_to_device(host, 'ring', device):
                 if bypass:
                     ex._bypass = True
                     try: ex.model(x.contiguous(memory_format=torch.channels_last) if channels_last else x)
@@ -737,7 +800,14 @@ def e2e_calibration_benchmark(batch: int, batches: int, steps: int, warmup: int,
     dgaps = [slow[i][3].elapsed_time(slow[i + 1][3]) for i in range(len(slow) - 1)]
     hi, di = max(range(len(gaps)), key=gaps.__getitem__), max(range(len(dgaps)), key=dgaps.__getitem__)
     where = lambda i: f'phase {slow[i][0]} batch {slow[i][1]}' if slow[i][1] < batches else f'phase {slow[i][0]} end (exchange / search)'   # noqa: E731
-    slowest = {'ms': round(max(step_ms), 3), 'host_enqueue_gap_ms': {'median': round(sorted(gaps)[len(gaps) // 2], 3), 'max': round(gaps[hi], 3), 'at': where(hi)},
+    worst = max(range(len(step_ms)), key=lambda i: step_ms[i])
+    cpu_in_gap = (slow[hi + 1][4] - slow[hi][4]) * 1e3                       # CPU time the enqueueing thread burnt inside its longest gap: ~gap = busy, ~0 = blocked / descheduled
+    slowest = {'ms': round(max(step_ms), 3), 'host_enqueue_gap_ms': {'median': round(sorted(gaps)[len(gaps) // 2], 3), 'max': round(gaps[hi], 3), 'at': where(hi),
+                                                                     'thread_cpu_ms_inside': round(cpu_in_gap, 3)},
+               'gaps_over_3x_median': sum(1 for g_ in gaps if g_ > 3 * sorted(gaps)[len(gaps) // 2]),
+               'allocator': {'cudaMalloc_calls': counters[worst + 1][0] - counters[worst][0], 'cudaFree_calls': counters[worst + 1][1] - counters[worst][1],
+                             'alloc_retries': counters[worst + 1][2] - counters[worst][2], 'reserved_gb': round(counters[worst + 1][3] / 2**30, 2),
+                             'cudaMalloc_calls_all_steps': counters[-1][0] - counters[0][0]},
                'device_gap_ms': {'median': round(sorted(dgaps)[len(dgaps) // 2], 3), 'max': round(dgaps[di], 3), 'at': where(di)}}
     total = ms / steps
     return {'value': round(world * steps * batches * batch / (ms * 1e-3), 1), 'unit': 'imgs/s',

@@ -167,6 +167,11 @@ def test_executor_calibration_paths_agree(ext):
     host = [d.cpu().pin_memory() for d in data]
     cal5 = calibrate_arena(ex5, host, method='kl', to_device=lambda t: t.to('cuda', non_blocking=True), prefetch=True)
     assert torch.equal(cal5.minmax, cal.minmax) and torch.equal(cal5.hist, cal.hist) and torch.equal(cal5.scale, s1)
+    ex6 = build()                                                           # the same through the persistent two-slot device ring (bench.py's e2e path),
+    cal6 = calibrate_arena(ex6, host, method='kl', to_device='ring')        # ... whose buffers are overwritten two batches later: nothing may read them late
+    assert torch.equal(cal6.minmax, cal.minmax) and torch.equal(cal6.hist, cal.hist) and torch.equal(cal6.scale, s1)
+    cal7 = calibrate_arena(build(), host, method='kl', to_device='ring', deferred=False)
+    assert torch.equal(cal7.hist, cal.hist)
     assert all(c.state == QuantizationStates.ACTIVATED for c in ex2.observed_configs_all())
     # evaluation loop (graphwise error analysis): per-op SNR of the quantised network vs fp32, all below the reference's 0.1 bar
     from ppq_b200.executor import graphwise_error_analyse
