@@ -5,9 +5,15 @@ cd "$(dirname "$0")/.."
 # final build (calls D / E) wins over the first pass (call A), which is kept as r02_first_pass_* where the numbers changed
 for f in r2_kbench_lc_old.txt; do [ -s gpurun_out/$f ] && cp gpurun_out/$f profiles/${f/r2_/r02_}; done
 [ -s gpurun_out/r2_kbench.txt ] && cp gpurun_out/r2_kbench.txt profiles/r02_first_pass_kbench.txt
-for f in r2d_tests.log r2d_kbench.txt r2d_kbench_kl_old.txt r2d_vs_reference_kernels.md r2d_bench_n1.json r2d_bench_ref_n1.json r2d_bench_yolo_n1.json r2d_launches.csv r2e_kbench_quantile.txt r2e_bench_e2e10.json r2b_bench_yolo_ref.json; do
+for f in r2d_tests.log r2d_kbench.txt r2d_kbench_kl_old.txt r2d_vs_reference_kernels.md r2d_bench_ref_n1.json r2d_launches.csv r2e_kbench_quantile.txt r2e_bench_e2e10.json r2b_bench_yolo_ref.json; do
   [ -s gpurun_out/$f ] && cp gpurun_out/$f profiles/$(echo $f | sed 's/^r2[a-e]_/r02_/')
 done
+# the bench lines of the final build (call F: inputs through the device ring)
+for f in r2f_bench_n1.json r2f_bench_yolo_n1.json r2f_bench_e2e_1.json r2f_bench_e2e_2.json r2g_bench_n1.json r2g_bench_n2.json; do
+  [ -s gpurun_out/$f ] && cp gpurun_out/$f profiles/$(echo $f | sed 's/^r2[a-g]_/r02_/')
+done
+[ -s gpurun_out/r2e_bench_e2e10.json ] && cp gpurun_out/r2e_bench_e2e10.json profiles/r02_before_ring_bench_e2e10.json
+rm -f profiles/r02_bench_e2e10.json
 python tools/launch_list_summary.py profiles/r02_launches.csv > profiles/r02_launches.md 2>/dev/null
 for f in gpurun_out/r2_scale_*.json; do [ -s "$f" ] && cp "$f" profiles/$(basename ${f/r2_/r02_}); done
 summ() { [ -s gpurun_out/$1.ncu-rep ] && python tools/ncu_summary.py gpurun_out/$1.ncu-rep "$2" > profiles/${1/r2_prof_/r02_}.md 2>/dev/null && echo "profiles/${1/r2_prof_/r02_}.md"; }
