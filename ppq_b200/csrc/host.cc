@@ -18,6 +18,7 @@ static int key_of(const char *name) {
     if (!strcmp(name, "minmax")) return kVarMinMax;
     if (!strcmp(name, "linear_quant_c")) return kVarChannel;
     if (!strcmp(name, "kl_search")) return kVarKlSearch;
+    if (!strcmp(name, "select")) return kVarSelect;
     return -1;
 }
 }  // namespace ppqb

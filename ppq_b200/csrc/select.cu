@@ -25,6 +25,7 @@
 // No allocation -- the caller provides the workspace.  The result is the identical element, bit for bit, except that a selected zero is
 // reported with the sign its key order gives (-0.0 < +0.0), equal as a float to whichever zero the reference's sort left at that index.
 #include "common.cuh"
+#include "variants.h"
 #include "../../include/ppq_b200.h"
 
 namespace ppqb {
@@ -243,7 +244,7 @@ __device__ __forceinline__ bool level_needed(const SelectState *st) {
 
 // One pass over the part [a, b) of a tensor for the CTA (`first`, `stride` in threads of the cooperating group).  Returns false when the
 // tensor needs nothing at this level (uniform over the grid).
-template <int LEVEL, int TPB>
+template <int LEVEL, int TPB, int U = 4, bool SEG = (LEVEL != 0)>
 __device__ __forceinline__ bool select_pass(const float *__restrict__ x, int64_t a, int64_t b, int64_t first, int64_t stride,
                                             SelectState *__restrict__ st, uint32_t *__restrict__ bufs, int64_t cap, int (*sh)[kDigits], unsigned int *sh_cnt) {
     constexpr int shift = level_shift(LEVEL);
@@ -286,7 +287,7 @@ __device__ __forceinline__ bool select_pass(const float *__restrict__ x, int64_t
         count(order_key(v.x)); count(order_key(v.y)); count(order_key(v.z)); count(order_key(v.w));
     };
     auto visit1 = [&](float f) { count(order_key(f)); };
-    stream_range<4, LEVEL != 0>(x, a, b, first, stride, visit4, visit1);
+    stream_range<U, SEG>(x, a, b, first, stride, visit4, visit1);
     __syncthreads();
     // flush: histograms with global atomics on the non-empty digits, staged keys after one reservation per CTA and rank
     __shared__ unsigned int s_base[2];
@@ -412,13 +413,13 @@ multi_select_pass0_spec_kernel(const ppq_b200_tensor_desc *__restrict__ descs, i
 }
 
 // ---- single tensor: the whole grid interleaves over the tensor, the last CTA to finish resolves the pass ------------------------------
-template <int LEVEL, int TPB>
-__global__ void __launch_bounds__(TPB, LEVEL == 0 ? 2 : 6)
+template <int LEVEL, int TPB, int U = 4, bool SEG = (LEVEL != 0), int CTAS = (LEVEL == 0 ? 2 : 6)>
+__global__ void __launch_bounds__(TPB, CTAS)
 select_pass_kernel(const float *__restrict__ x, int64_t n, SelectState *__restrict__ st, uint32_t *__restrict__ bufs, int64_t cap) {
     __shared__ int sh[2][kDigits];
     __shared__ unsigned int sh_cnt[2];
     __shared__ bool is_last;
-    if (!select_pass<LEVEL, TPB>(x, 0, n, (int64_t)blockIdx.x * TPB + threadIdx.x, (int64_t)gridDim.x * TPB, st, bufs, cap, sh, sh_cnt)) return;
+    if (!select_pass<LEVEL, TPB, U, SEG>(x, 0, n, (int64_t)blockIdx.x * TPB + threadIdx.x, (int64_t)gridDim.x * TPB, st, bufs, cap, sh, sh_cnt)) return;
     // every CTA's atomics are ordered before its ticket
     __threadfence();
     __syncthreads();
@@ -545,8 +546,22 @@ static int select_two(const float *x, int64_t n, int q_mode, float q, long long 
     if (guess) {
         const int g0 = grid_pass0(n);
         select_pass0_spec_kernel<<<g0 > sm_count() ? sm_count() : g0, kSelThreads, 0, s>>>(x, n, st, bufs, cap);
-    } else select_pass_kernel<0, kSelThreads><<<grid_pass0(n), kSelThreads, 0, s>>>(x, n, st, bufs, cap);
-    select_pass_kernel<1, kFilterThreads><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
+    } else {
+        switch (variant_of(kVarSelect) & 7) {                              // A/B knobs of pass 0 (variants.h)
+        case 1: select_pass_kernel<0, kSelThreads, 2><<<grid_pass0(n), kSelThreads, 0, s>>>(x, n, st, bufs, cap); break;
+        case 2: select_pass_kernel<0, kSelThreads, 4, true><<<grid_pass0(n), kSelThreads, 0, s>>>(x, n, st, bufs, cap); break;
+        case 3: select_pass_kernel<0, kSelThreads, 2, true><<<grid_pass0(n), kSelThreads, 0, s>>>(x, n, st, bufs, cap); break;
+        case 4: select_pass_kernel<0, 512, 4, false, 4><<<grid_pass0(n) * 2, 512, 0, s>>>(x, n, st, bufs, cap); break;
+        default: select_pass_kernel<0, kSelThreads><<<grid_pass0(n), kSelThreads, 0, s>>>(x, n, st, bufs, cap);
+        }
+    }
+    switch (variant_of(kVarSelect) >> 3) {                                 // ... and of pass 1
+    case 1: select_pass_kernel<1, kFilterThreads, 2><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap); break;
+    case 2: select_pass_kernel<1, 512, 4, true, 3><<<grid_filter(n) / 2, 512, 0, s>>>(x, n, st, bufs, cap); break;
+    case 3: select_pass_kernel<1, 1024, 2, true, 2><<<grid_pass0(n), 1024, 0, s>>>(x, n, st, bufs, cap); break;
+    case 4: select_pass_kernel<1, kFilterThreads, 4, false><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap); break;
+    default: select_pass_kernel<1, kFilterThreads><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
+    }
     // pass 2 is rarely needed (a bucket too big to compact that holds several distinct values): two CTAs per SM keep its usual early exit cheap
     const int g2 = grid_filter(n) > 2 * sm_count() ? 2 * sm_count() : grid_filter(n);
     select_pass_kernel<2, kFilterThreads><<<g2, kFilterThreads, 0, s>>>(x, n, st, bufs, cap);
