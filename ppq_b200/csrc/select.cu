@@ -84,26 +84,6 @@ __device__ __forceinline__ long long quantile_rank(int64_t n, float frac) {
     return pos < 0 ? 0 : pos;
 }
 
-// one CTA per tensor.  q_mode: ranks = {rn(n q), rn(n (1 - q))};  otherwise explicit ranks (isotone)
-__global__ void select_init_kernel(SelectState *states, const ppq_b200_tensor_desc *descs, int64_t n_single, float q, int q_mode,
-                                   long long r0, long long r1, const uint32_t *__restrict__ guess = nullptr) {
-    SelectState *st = states + blockIdx.x;
-    for (int i = threadIdx.x; i < 2 * kDigits; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
-    if (threadIdx.x == 0) {
-        const int64_t n = descs ? descs[blockIdx.x].n : n_single;
-        if (q_mode) { r0 = quantile_rank(n, q); r1 = quantile_rank(n, 1.0f - q); }
-        st->prefix[0] = st->prefix[1] = 0u; st->mode[0] = st->mode[1] = kModeHist; st->shared = 1u; st->done = 0u;
-        st->ccount[0] = st->ccount[1] = 0u; st->cbuf[0] = 0u; st->cbuf[1] = 1u; st->clevel[0] = st->clevel[1] = 0u;
-        st->compacted[0] = st->compacted[1] = 0u; st->kmin[0] = st->kmin[1] = 0xFFFFFFFFu; st->kmax[0] = st->kmax[1] = 0u;
-        st->rank[0] = r0; st->rank[1] = r1; st->count[0] = st->count[1] = n;
-        st->spec = guess ? 1u : 0u; st->eqc[0] = st->eqc[1] = 0u; st->veq[0] = st->veq[1] = 0u; st->vkey[0] = st->vkey[1] = 0u;
-        if (guess) {
-            const uint32_t *gw = guess + (descs ? (int64_t)descs[blockIdx.x].slot : 0) * kGuessWords;
-            st->g[0] = gw[0]; st->k[0] = gw[1]; st->d[0] = gw[2]; st->g[1] = gw[4]; st->k[1] = gw[5]; st->d[1] = gw[6];
-        } else { st->g[0] = st->k[0] = 0xFFFFFFFFu; st->g[1] = st->k[1] = 0u; st->d[0] = st->d[1] = kSpecMarginInit; }
-    }
-}
-
 // Block-wide search of the bucket that contains rank k in a 2048-bin histogram (TPB threads, kDigits / TPB consecutive bins per thread, warp
 // shuffles).  Exactly one (thread, bin) matches because k < total.  Results through shared memory; ends with a barrier.
 template <int TPB, class Load>
@@ -128,6 +108,96 @@ __device__ __forceinline__ void block_pick(Load &&load, unsigned long long k, un
         before += c[j];
     }
     __syncthreads();
+}
+
+// ---- self-speculation: thresholds from a sample ------------------------------------------------------------------------------------------
+// A cold call has no thresholds from a previous batch.  For a big tensor the init CTA draws kSampleKeys elements (one per stride window, at a
+// hashed offset inside the window so that no channel / row period can alias with the stride), selects the j-th largest and j-th smallest sample
+// exactly (three 11/11/10-bit rounds in shared memory) and uses them as this call's thresholds: the tail beyond the j-th largest of m samples
+// holds Gamma(j) x n / m elements, so with j = max(16, 3 x need x m / n) it contains the `need` wanted elements with overwhelming probability and
+// stays far below the compaction buffer.  Copies of the threshold key itself are only counted (k = g), which covers post-ReLU zeros and clipped
+// maxima.  A wrong guess costs nothing but the sample: select_scan<0> then falls back to the regular passes.
+constexpr int kSampleKeys = 16384;
+constexpr int64_t kSampleMinElems = (int64_t)1 << 23;
+
+__host__ __device__ inline long long sample_rank_from_end(long long need, int64_t n) {     // j
+    const long long j = (3 * need * kSampleKeys + n - 1) / n;
+    return j < 16 ? 16 : j;
+}
+__host__ __device__ inline bool sample_rank_ok(long long j, int64_t n, int64_t cap) {
+    return j <= kSampleKeys / 4 && 3 * j * (n / kSampleKeys) <= 2 * cap;                   // mean tail x 1.5 fits the buffer
+}
+
+// both order statistics (ascending ranks rk[0], rk[1]) of the CTA's kSampleKeys keys (PER per thread, 1024 threads), exact
+template <int PER>
+__device__ __forceinline__ void cta_select_two(const uint32_t (&key)[PER], long long rk0, long long rk1, uint32_t *out0, uint32_t *out1) {
+    __shared__ int sh[2][kDigits];
+    __shared__ unsigned int s_digit;
+    __shared__ unsigned long long s_before, s_cnt;
+    uint32_t pre[2] = {0u, 0u};
+    unsigned long long rk[2] = {(unsigned long long)rk0, (unsigned long long)rk1};
+#pragma unroll
+    for (int level = 0; level < 3; level++) {
+        const int shift = level_shift(level);
+        const uint32_t dmask = level_dmask(level), pmask = level_pmask(level);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * kDigits; i += blockDim.x) (&sh[0][0])[i] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const uint32_t k = key[j], d = (k >> shift) & dmask;
+            if ((k & pmask) == pre[0]) atomicAdd(&sh[0][d], 1);
+            if ((k & pmask) == pre[1]) atomicAdd(&sh[1][d], 1);
+        }
+        __syncthreads();
+        for (int r = 0; r < 2; r++) {
+            block_pick<1024>([&](int i) { return (unsigned long long)sh[r][i]; }, rk[r], &s_digit, &s_before, &s_cnt);
+            pre[r] |= s_digit << shift;
+            rk[r] -= s_before;
+        }
+    }
+    *out0 = pre[0]; *out1 = pre[1];
+}
+
+// one CTA per tensor.  q_mode: ranks = {rn(n q), rn(n (1 - q))};  otherwise explicit ranks (isotone).  x_sample != nullptr (single tensor,
+// 1024 threads): thresholds from a sample unless the caller's guess already holds some.
+__global__ void __launch_bounds__(1024)
+select_init_kernel(SelectState *states, const ppq_b200_tensor_desc *descs, int64_t n_single, float q, int q_mode,
+                   long long r0, long long r1, const uint32_t *__restrict__ guess = nullptr, const float *__restrict__ x_sample = nullptr, int64_t cap = 0) {
+    SelectState *st = states + blockIdx.x;
+    for (int i = threadIdx.x; i < 2 * kDigits; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
+    const int64_t n = descs ? descs[blockIdx.x].n : n_single;
+    if (q_mode) { r0 = quantile_rank(n, q); r1 = quantile_rank(n, 1.0f - q); }
+    const uint32_t *gw = guess ? guess + (descs ? (int64_t)descs[blockIdx.x].slot : 0) * kGuessWords : nullptr;
+    uint32_t g_hi = 0xFFFFFFFFu, k_hi = 0xFFFFFFFFu, g_lo = 0u, k_lo = 0u, d_hi = kSpecMarginInit, d_lo = kSpecMarginInit;
+    if (gw) { g_hi = gw[0]; k_hi = gw[1]; d_hi = gw[2]; g_lo = gw[4]; k_lo = gw[5]; d_lo = gw[6]; }
+    unsigned int spec = guess ? 1u : 0u;
+    if (x_sample && g_hi == 0xFFFFFFFFu && g_lo == 0u) {               // uniform over the CTA: nothing guessed yet
+        constexpr int PER = kSampleKeys / 1024;
+        const int64_t stride = n / kSampleKeys;
+        uint32_t key[PER];
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const uint32_t i = (uint32_t)(j * 1024 + threadIdx.x);
+            const int64_t off = (int64_t)((uint64_t)(i * 0x9E3779B1u) % (uint64_t)stride);
+            key[j] = order_key(__ldg(x_sample + (int64_t)i * stride + off));
+        }
+        const long long j_hi = sample_rank_from_end(n - r0, n), j_lo = sample_rank_from_end(r1 + 1, n);
+        const bool ok_hi = sample_rank_ok(j_hi, n, cap), ok_lo = sample_rank_ok(j_lo, n, cap);
+        uint32_t s_hi, s_lo;
+        cta_select_two<PER>(key, ok_hi ? kSampleKeys - j_hi : 0, ok_lo ? j_lo - 1 : 0, &s_hi, &s_lo);
+        if (ok_hi) g_hi = k_hi = s_hi;
+        if (ok_lo) g_lo = k_lo = s_lo;
+        spec = 1u;
+    }
+    if (threadIdx.x == 0) {
+        st->prefix[0] = st->prefix[1] = 0u; st->mode[0] = st->mode[1] = kModeHist; st->shared = 1u; st->done = 0u;
+        st->ccount[0] = st->ccount[1] = 0u; st->cbuf[0] = 0u; st->cbuf[1] = 1u; st->clevel[0] = st->clevel[1] = 0u;
+        st->compacted[0] = st->compacted[1] = 0u; st->kmin[0] = st->kmin[1] = 0xFFFFFFFFu; st->kmax[0] = st->kmax[1] = 0u;
+        st->rank[0] = r0; st->rank[1] = r1; st->count[0] = st->count[1] = n;
+        st->spec = spec; st->eqc[0] = st->eqc[1] = 0u; st->veq[0] = st->veq[1] = 0u; st->vkey[0] = st->vkey[1] = 0u;
+        st->g[0] = g_hi; st->k[0] = k_hi; st->d[0] = d_hi; st->g[1] = g_lo; st->k[1] = k_lo; st->d[1] = d_lo;
+    }
 }
 
 // Resolve a pass for one tensor: run by the last CTA to finish its part of that tensor (ticket counter), in both the single-tensor and the table form.
@@ -542,8 +612,15 @@ static int select_two(const float *x, int64_t n, int q_mode, float q, long long 
     SelectState *st = (SelectState *)workspace;
     uint32_t *bufs = (uint32_t *)(st + 1);
     const int64_t cap = kDefaultCap;
-    select_init_kernel<<<1, 1024, 0, s>>>(st, nullptr, n, q, q_mode, r0, r1, guess);
-    if (guess) {
+    // cold call on a big tensor: thresholds from a sample (select_init_kernel), unless both tails are too heavy for the compaction buffer
+    bool sample = false;
+    if (q_mode && n >= kSampleMinElems && !(variant_of(kVarSelect) & 64)) {
+        auto rank_of = [&](float frac) { long long pos = (long long)nearbyintf((float)n * frac); pos = pos > n - 1 ? n - 1 : pos; return pos < 0 ? 0 : pos; };
+        const long long need_hi = n - rank_of(q), need_lo = rank_of(1.0f - q) + 1;
+        sample = sample_rank_ok(sample_rank_from_end(need_hi, n), n, cap) || sample_rank_ok(sample_rank_from_end(need_lo, n), n, cap);
+    }
+    select_init_kernel<<<1, 1024, 0, s>>>(st, nullptr, n, q, q_mode, r0, r1, guess, sample ? x : nullptr, cap);
+    if (guess || sample) {
         const int g0 = grid_pass0(n);
         select_pass0_spec_kernel<<<g0 > sm_count() ? sm_count() : g0, kSelThreads, 0, s>>>(x, n, st, bufs, cap);
     } else {
@@ -555,7 +632,7 @@ static int select_two(const float *x, int64_t n, int q_mode, float q, long long 
         default: select_pass_kernel<0, kSelThreads><<<grid_pass0(n), kSelThreads, 0, s>>>(x, n, st, bufs, cap);
         }
     }
-    switch (variant_of(kVarSelect) >> 3) {                                 // ... and of pass 1
+    switch ((variant_of(kVarSelect) >> 3) & 7) {                                 // ... and of pass 1
     case 1: select_pass_kernel<1, kFilterThreads, 2><<<grid_filter(n), kFilterThreads, 0, s>>>(x, n, st, bufs, cap); break;
     case 2: select_pass_kernel<1, 512, 4, true, 3><<<grid_filter(n) / 2, 512, 0, s>>>(x, n, st, bufs, cap); break;
     case 3: select_pass_kernel<1, 1024, 2, true, 2><<<grid_pass0(n), 1024, 0, s>>>(x, n, st, bufs, cap); break;

@@ -7,7 +7,7 @@
 //   "linear_quant_c": 0 default (shared-memory operator table for rows shorter than 512 elements) | 1 the round-1 per-vector operator rebuild
 //   "kl_search": 0 default (one warp per candidate) | 1 the serial-candidate kernel
 //   "select": single-tensor radix select A/B: low 3 bits = pass 0 (0 default: 2 x 1024 threads per SM, 4 interleaved loads | 1 two loads | 2 warp segments, 4 loads
-//             | 3 warp segments, 2 loads | 4 four 512-thread CTAs), bits 3+ = pass 1 (0 default: 6 x 256 threads, warp segments, 4 loads | 1 two loads | 2 3 x 512 threads | 3 2 x 1024 threads, 2 loads | 4 interleaved)
+//             | 3 warp segments, 2 loads | 4 four 512-thread CTAs), bits 3-5 = pass 1 (0 default: 6 x 256 threads, warp segments, 4 loads | 1 two loads | 2 3 x 512 threads | 3 2 x 1024 threads, 2 loads | 4 interleaved), bit 6 (64) = no thresholds from a sample on cold calls
 #pragma once
 namespace ppqb {
 enum { kVarLinearT = 0, kVarHistogram = 1, kVarMinMax = 2, kVarChannel = 3, kVarKlSearch = 4, kVarSelect = 5, kVarCount = 8 };

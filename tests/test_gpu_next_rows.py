@@ -102,6 +102,48 @@ def test_multi_tensor_quantile_matches_single_launches(ext):
         ext.Multi_Quantile_T(descs, max(sizes), 0.5, torch.zeros(len(xs), 2, device='cuda'), 2, torch.empty(16, dtype=torch.uint8, device='cuda'), 64, None)
 
 
+def test_cold_quantile_with_thresholds_from_a_sample(ext, ref):
+    """Tensors of >= 8 M elements: a cold Quantile_T draws 16384 samples in its init CTA and speculates on thresholds derived from them (select.cu,
+    "self-speculation").  Whatever the sample says, the result must be the exact order statistics: well-behaved data, post-ReLU zeros and clipped
+    maxima (the threshold key itself is massively repeated), a constant, few outliers the sample cannot see, structure with the sampling period,
+    and -- with the sample positions reproduced here -- values planted exactly where the sampler looks, which makes its thresholds useless."""
+    g = torch.Generator(device='cuda').manual_seed(21)
+    n = (1 << 23) + 4099
+    m, stride = 16384, ((1 << 23) + 4099) // 16384
+    i = torch.arange(m, dtype=torch.int64)
+    pos = (i * stride + ((i * 0x9E3779B1) % (1 << 32)) % stride).cuda()     # the sampler's positions: one per stride window at a hashed offset
+
+    def check(x, q, tag):
+        got = ext.Quantile_T(x, q)
+        srt = torch.sort(x)[0]
+        ia = int(min(max(np.rint(np.float32(n) * np.float32(q)), 0), n - 1)); ib = int(min(max(np.rint(np.float32(n) * (np.float32(1) - np.float32(q))), 0), n - 1))
+        assert torch.equal(got, torch.stack([srt[ia], srt[ib]])), (tag, q, got, srt[ia], srt[ib])
+        if ref is not None: assert torch.equal(got, ref.Quantile_T(x, q)), (tag, q)
+        ext.set_variant('select', 64)                                        # the same call without the sample: the regular two-pass route
+        try: assert torch.equal(ext.Quantile_T(x, q), got), (tag, q)
+        finally: ext.set_variant('select', 0)
+
+    base = torch.randn(n, device='cuda', generator=g) * 2
+    cases = {'randn': base, 'relu': torch.relu(base), 'relu6-like': torch.clamp(base, 0.0, 1.5), 'const': torch.full((n,), 0.75, device='cuda')}
+    x = torch.zeros(n, device='cuda'); x[:700] = 5.0 + torch.rand(700, device='cuda', generator=g); x[-300:] = -3.0
+    cases['outliers the sample cannot see'] = x
+    cases['period of the stride'] = (torch.arange(n, device='cuda') % stride).float()
+    x = base.clone(); x[pos[:64]] = 1e6; x[pos[64:128]] = -1e6                 # the sampler sees 64 huge values: its thresholds keep ~64 candidates, far fewer than needed
+    cases['planted at the sample positions'] = x
+    x = torch.relu(base); x[pos] = 3.0                                         # every sample is the same mid-range value: both thresholds equal 3.0
+    cases['all samples equal'] = x
+    for tag, x in cases.items():
+        for q in (0.9999, 0.99999, 0.999, 0.99):
+            check(x, q, tag)
+    # the first call with a guess buffer samples too, later calls use the remembered thresholds
+    guess = ext.Quantile_Guess_Init(1, torch.zeros(1, device='cuda'))
+    for step in range(3):
+        x = torch.relu(torch.randn(n, device='cuda', generator=g)) * (1 + 0.05 * step)
+        srt = torch.sort(x)[0]
+        ia = int(np.rint(np.float32(n) * np.float32(0.9999))); ib = int(np.rint(np.float32(n) * (np.float32(1) - np.float32(0.9999))))
+        assert torch.equal(ext.Quantile_T_Guess(x, 0.9999, guess), torch.stack([srt[ia], srt[ib]])), step
+
+
 def test_speculative_quantile_over_consecutive_batches(ext):
     """With a `guess` buffer the select compacts, during its first pass, the keys beyond the thresholds remembered from the previous call of the
     same slot -- consecutive calibration batches of one activation then need ONE pass over the tensor.  Whatever the guess is worth (first call,
