@@ -111,8 +111,8 @@ __device__ __forceinline__ void block_pick(Load &&load, unsigned long long k, un
 }
 
 // ---- self-speculation: thresholds from a sample ------------------------------------------------------------------------------------------
-// A cold call has no thresholds from a previous batch.  For a big tensor the init CTA draws kSampleKeys elements (one per stride window, at a
-// hashed offset inside the window so that no channel / row period can alias with the stride), selects the j-th largest and j-th smallest sample
+// A cold call has no thresholds from a previous batch.  For a big tensor a small grid draws kSampleKeys elements (one per stride window, at a
+// hashed offset inside the window so that no channel / row period can alias with the stride), the init CTA selects the j-th largest and j-th smallest sample
 // exactly (three 11/11/10-bit rounds in shared memory) and uses them as this call's thresholds: the tail beyond the j-th largest of m samples
 // holds Gamma(j) x n / m elements, so with j = max(16, 3 x need x m / n) it contains the `need` wanted elements with overwhelming probability and
 // stays far below the compaction buffer.  Copies of the threshold key itself are only counted (k = g), which covers post-ReLU zeros and clipped
@@ -159,11 +159,20 @@ __device__ __forceinline__ void cta_select_two(const uint32_t (&key)[PER], long 
     *out0 = pre[0]; *out1 = pre[1];
 }
 
-// one CTA per tensor.  q_mode: ranks = {rn(n q), rn(n (1 - q))};  otherwise explicit ranks (isotone).  x_sample != nullptr (single tensor,
-// 1024 threads): thresholds from a sample unless the caller's guess already holds some.
+// The sample itself is drawn by a grid of small CTAs (16 K scattered 32-byte sectors are ~25 us for one SM's miss queue and ~2 us for 64 SMs).
+__global__ void __launch_bounds__(256)
+select_sample_kernel(const float *__restrict__ x, int64_t n, uint32_t *__restrict__ keys) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    const int64_t stride = n / kSampleKeys;
+    const int64_t off = (int64_t)((uint64_t)(i * 0x9E3779B1u) % (uint64_t)stride);
+    keys[i] = order_key(__ldg(x + (int64_t)i * stride + off));
+}
+
+// one CTA per tensor.  q_mode: ranks = {rn(n q), rn(n (1 - q))};  otherwise explicit ranks (isotone).  sample_keys != nullptr (single tensor,
+// 1024 threads): thresholds from the sample unless the caller's guess already holds some.
 __global__ void __launch_bounds__(1024)
 select_init_kernel(SelectState *states, const ppq_b200_tensor_desc *descs, int64_t n_single, float q, int q_mode,
-                   long long r0, long long r1, const uint32_t *__restrict__ guess = nullptr, const float *__restrict__ x_sample = nullptr, int64_t cap = 0) {
+                   long long r0, long long r1, const uint32_t *__restrict__ guess = nullptr, const uint32_t *__restrict__ sample_keys = nullptr, int64_t cap = 0) {
     SelectState *st = states + blockIdx.x;
     for (int i = threadIdx.x; i < 2 * kDigits; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
     const int64_t n = descs ? descs[blockIdx.x].n : n_single;
@@ -172,16 +181,11 @@ select_init_kernel(SelectState *states, const ppq_b200_tensor_desc *descs, int64
     uint32_t g_hi = 0xFFFFFFFFu, k_hi = 0xFFFFFFFFu, g_lo = 0u, k_lo = 0u, d_hi = kSpecMarginInit, d_lo = kSpecMarginInit;
     if (gw) { g_hi = gw[0]; k_hi = gw[1]; d_hi = gw[2]; g_lo = gw[4]; k_lo = gw[5]; d_lo = gw[6]; }
     unsigned int spec = guess ? 1u : 0u;
-    if (x_sample && g_hi == 0xFFFFFFFFu && g_lo == 0u) {               // uniform over the CTA: nothing guessed yet
+    if (sample_keys && g_hi == 0xFFFFFFFFu && g_lo == 0u) {            // uniform over the CTA: nothing guessed yet
         constexpr int PER = kSampleKeys / 1024;
-        const int64_t stride = n / kSampleKeys;
         uint32_t key[PER];
 #pragma unroll
-        for (int j = 0; j < PER; j++) {
-            const uint32_t i = (uint32_t)(j * 1024 + threadIdx.x);
-            const int64_t off = (int64_t)((uint64_t)(i * 0x9E3779B1u) % (uint64_t)stride);
-            key[j] = order_key(__ldg(x_sample + (int64_t)i * stride + off));
-        }
+        for (int j = 0; j < PER; j++) key[j] = __ldcg(sample_keys + j * 1024 + threadIdx.x);
         const long long j_hi = sample_rank_from_end(n - r0, n), j_lo = sample_rank_from_end(r1 + 1, n);
         const bool ok_hi = sample_rank_ok(j_hi, n, cap), ok_lo = sample_rank_ok(j_lo, n, cap);
         uint32_t s_hi, s_lo;
@@ -619,7 +623,9 @@ static int select_two(const float *x, int64_t n, int q_mode, float q, long long 
         const long long need_hi = n - rank_of(q), need_lo = rank_of(1.0f - q) + 1;
         sample = sample_rank_ok(sample_rank_from_end(need_hi, n), n, cap) || sample_rank_ok(sample_rank_from_end(need_lo, n), n, cap);
     }
-    select_init_kernel<<<1, 1024, 0, s>>>(st, nullptr, n, q, q_mode, r0, r1, guess, sample ? x : nullptr, cap);
+    uint32_t *sample_keys = bufs + 2 * cap;
+    if (sample) select_sample_kernel<<<kSampleKeys / 256, 256, 0, s>>>(x, n, sample_keys);
+    select_init_kernel<<<1, 1024, 0, s>>>(st, nullptr, n, q, q_mode, r0, r1, guess, sample ? sample_keys : nullptr, cap);
     if (guess || sample) {
         const int g0 = grid_pass0(n);
         select_pass0_spec_kernel<<<g0 > sm_count() ? sm_count() : g0, kSelThreads, 0, s>>>(x, n, st, bufs, cap);
@@ -652,7 +658,7 @@ using namespace ppqb;
 
 extern "C" {
 
-int64_t ppq_b200_quantile_workspace_bytes(void) { return (int64_t)sizeof(SelectState) + 2 * kDefaultCap * (int64_t)sizeof(uint32_t); }
+int64_t ppq_b200_quantile_workspace_bytes(void) { return (int64_t)sizeof(SelectState) + (2 * kDefaultCap + kSampleKeys) * (int64_t)sizeof(uint32_t); }
 
 int64_t ppq_b200_quantile_guess_words(void) { return kGuessWords; }
 
