@@ -114,7 +114,7 @@ __device__ __forceinline__ void block_pick(Load &&load, unsigned long long k, un
 // A cold call has no thresholds from a previous batch.  For a big tensor a small grid draws kSampleKeys elements (one per stride window, at a
 // hashed offset inside the window so that no channel / row period can alias with the stride), the init CTA selects the j-th largest and j-th smallest sample
 // exactly (three 11/11/10-bit rounds in shared memory) and uses them as this call's thresholds: the tail beyond the j-th largest of m samples
-// holds Gamma(j) x n / m elements, so with j = max(16, 3 x need x m / n) it contains the `need` wanted elements with overwhelming probability and
+// holds Gamma(j) x n / m elements, so with j = max(12, 3 x need x m / n) it contains the `need` wanted elements with overwhelming probability and
 // stays far below the compaction buffer.  Copies of the threshold key itself are only counted (k = g), which covers post-ReLU zeros and clipped
 // maxima.  A wrong guess costs nothing but the sample: select_scan<0> then falls back to the regular passes.
 constexpr int kSampleKeys = 16384;
@@ -122,7 +122,7 @@ constexpr int64_t kSampleMinElems = (int64_t)1 << 23;
 
 __host__ __device__ inline long long sample_rank_from_end(long long need, int64_t n) {     // j
     const long long j = (3 * need * kSampleKeys + n - 1) / n;
-    return j < 16 ? 16 : j;
+    return j < 12 ? 12 : j;
 }
 __host__ __device__ inline bool sample_rank_ok(long long j, int64_t n, int64_t cap) {
     return j <= kSampleKeys / 4 && 3 * j * (n / kSampleKeys) <= 2 * cap;                   // mean tail x 1.5 fits the buffer
@@ -571,17 +571,40 @@ select_finish_kernel(const SelectState *__restrict__ states, const uint32_t *__r
         const uint32_t *keys = bufs + ((int64_t)tensor * 2 + st->cbuf[r]) * cap;
         const unsigned m = st->ccount[st->cbuf[r]];
         unsigned long long k = (unsigned long long)st->rank[r];
+        // The first kFinishRegs x 1024 candidates live in registers for all three levels (a cold call that speculated on sampled thresholds
+        // brings ~40 K of them: re-reading them from L2 once per level, one dependent load per iteration, cost 15-20 us); the rest is
+        // streamed per level with 8 loads in flight.
+        constexpr int kFinishRegs = 32;
+        uint32_t held[kFinishRegs];
+        uint32_t valid = 0u;
+#pragma unroll
+        for (int j = 0; j < kFinishRegs; j++) {
+            const unsigned i = (unsigned)j * kSelThreads + threadIdx.x;
+            held[j] = 0u;
+            if (i < m) { held[j] = __ldcg(keys + i); valid |= 1u << j; }
+        }
+        const uint32_t vkey = st->vkey[r];
+        const unsigned veq = st->veq[r];
         for (int level = (int)st->clevel[r]; level <= 2; level++) {
             const int shift = level_shift(level);
-            const uint32_t dmask = level_dmask(level), pmask = level_pmask(level);
+            const uint32_t dmask = level_dmask(level), pmask = level_pmask(level), want = key & pmask;
             for (int i = threadIdx.x; i < kDigits; i += kSelThreads) sh[i] = 0;
             __syncthreads();
-            for (unsigned i = threadIdx.x; i < m; i += kSelThreads) {
-                const uint32_t v = __ldcg(keys + i);
-                if ((v & pmask) == (key & pmask)) atomicAdd(&sh[(v >> shift) & dmask], 1);
+#pragma unroll
+            for (int j = 0; j < kFinishRegs; j++)
+                if (((valid >> j) & 1u) && (held[j] & pmask) == want) atomicAdd(&sh[(held[j] >> shift) & dmask], 1);
+            for (unsigned base = kFinishRegs * kSelThreads; base < m; base += 8 * kSelThreads) {
+                uint32_t v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) { const unsigned i = base + (unsigned)j * kSelThreads + threadIdx.x; v[j] = i < m ? __ldcg(keys + i) : 0u; }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const unsigned i = base + (unsigned)j * kSelThreads + threadIdx.x;
+                    if (i < m && (v[j] & pmask) == want) atomicAdd(&sh[(v[j] >> shift) & dmask], 1);
+                }
             }
-            if (threadIdx.x == 0 && st->veq[r] && (st->vkey[r] & pmask) == (key & pmask))      // the counted-only copies of last call's key
-                atomicAdd(&sh[(st->vkey[r] >> shift) & dmask], (int)st->veq[r]);
+            if (threadIdx.x == 0 && veq && (vkey & pmask) == want)                            // the counted-only copies of the threshold key
+                atomicAdd(&sh[(vkey >> shift) & dmask], (int)veq);
             __syncthreads();
             block_pick<kSelThreads>([&](int i) { return (unsigned long long)sh[i]; }, k, &s_digit, &s_before, &s_cnt);
             key |= s_digit << shift;
