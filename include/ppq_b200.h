@@ -136,7 +136,9 @@ PPQ_B200_API int ppq_b200_histogram_t_dscale(const float *x, int64_t n, const fl
 /* replaces Quantile_T, sort.cu:6-20, 42-59 (ffi.py:171-176): out[0] = sorted[clip(rn(n*q))], out[1] = sorted[clip(rn(n*(1-q)))],
  * found by an exact radix select on the order-preserving key (no clone, no full sort; same element bit for bit): two streaming passes
  * over the tensor (top-digit histogram, then compaction of the two selected buckets) and a finish over the compacted keys; a third
- * pass only when a selected bucket does not fit the workspace and holds more than one distinct value.
+ * pass only when a selected bucket does not fit the workspace and holds more than one distinct value.  Tensors of >= 8 Mi elements
+ * first try to get away with ONE pass: thresholds derived from 16 Ki sampled elements decide which keys are compacted during the
+ * first pass; if they turn out not to contain the wanted order statistics, the regular passes follow (the result is exact either way).
  * `workspace` is DEVICE scratch of ppq_b200_quantile_workspace_bytes() bytes. */
 PPQ_B200_API int64_t ppq_b200_quantile_workspace_bytes(void);
 PPQ_B200_API int ppq_b200_quantile_t(const float *x, int64_t n, float q, float *out2, void *workspace, void *stream);
