@@ -19,7 +19,7 @@ rm -f profiles/r02_bench_e2e10.json
 [ -s gpurun_out/r2j_bench_n1.json ] && cp gpurun_out/r2j_bench_n1.json profiles/r02_bench_n1_final.json
 [ -s gpurun_out/r2d_vs_reference_kernels.md ] && cp gpurun_out/r2d_vs_reference_kernels.md profiles/r02_vs_reference_kernels_callD.md
 [ -s gpurun_out/r2j_vs_reference_kernels.md ] && cp gpurun_out/r2j_vs_reference_kernels.md profiles/r02_vs_reference_kernels.md
-[ -s gpurun_out/r2j_kbench_quantile.txt ] && cp gpurun_out/r2j_kbench_quantile.txt profiles/r02_kbench_quantile.txt
+[ -s gpurun_out/r2k_kbench_quantile.txt ] && cp gpurun_out/r2k_kbench_quantile.txt profiles/r02_kbench_quantile.txt
 [ -s gpurun_out/r2e_kbench_quantile.txt ] && cp gpurun_out/r2e_kbench_quantile.txt profiles/r02_kbench_quantile_before_sampling.txt
 [ -s gpurun_out/r2i_select_ab.txt ] && cp gpurun_out/r2i_select_ab.txt profiles/r02_select_ab.txt
 [ -s gpurun_out/r2h_select_ab.txt ] && cp gpurun_out/r2h_select_ab.txt profiles/r02_select_launch_shapes.txt
