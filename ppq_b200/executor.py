@@ -667,7 +667,7 @@ def graphwise_error_analyse(executor: TorchExecutor, batches, to_device=None, gr
     static_in, graph, fp, qt, static_snr = None, None, {}, {}, None
     try:
         for x in batches:
-            if to_device is not None: x = to_device(x)
+            if to_device is not None: x = x.to(next(executor.model.parameters()).device, non_blocking=True) if isinstance(to_device, str) else to_device(x)
             if not graphs:
                 fp, qt = {}, {}
                 both(x, fp, qt)

@@ -271,3 +271,50 @@ def test_multi_tensor_span_partitions_cover_every_element_exactly_once():
                                 seen[t][idx] += 1
                 t += 1
         assert all((s == 1).all() for s in seen), (it, ns, grid)
+
+
+def test_sampled_thresholds_contain_the_wanted_order_statistics():
+    """select.cu, "self-speculation": a cold Quantile_T on >= 8 Mi elements reads one element per stride window (hashed offset), takes the j-th largest
+    / smallest of the 16384 samples as thresholds (j = max(12, 3 x need x m / n)) and compacts what lies at or beyond them, counting copies of the
+    threshold key itself instead of storing them.  Twin of that rule on the CPU: for bell-shaped, post-ReLU, clipped and heavy-tailed data the
+    candidates always contain the `need` wanted elements and the stored ones fit the 256 Ki-key buffer -- i.e. the tensor is read once; for a sample
+    that lies (values planted exactly where the sampler looks) the verdict must be "failed", never a wrong selection."""
+    m, cap = 16384, 1 << 18
+    n = (1 << 23) + 4099
+    stride = n // m
+    i = np.arange(m, dtype=np.uint64)
+    pos = (i * np.uint64(stride) + ((i * np.uint64(0x9E3779B1)) % np.uint64(1 << 32)) % np.uint64(stride)).astype(np.int64)
+    assert pos.max() < n and np.all(np.diff(pos) > 0) and np.all(pos // stride == np.arange(m))     # one sample per window, inside the tensor
+
+    def rank_from_end(need): return max(12, -(-3 * need * m // n))
+    def rank_ok(j): return j <= m // 4 and 3 * j * (n // m) <= 2 * cap
+
+    def verdicts(x, q):
+        r0 = int(min(max(np.rint(np.float32(n) * np.float32(q)), 0), n - 1)); r1 = int(min(max(np.rint(np.float32(n) * (np.float32(1) - np.float32(q))), 0), n - 1))
+        need_hi, need_lo = n - r0, r1 + 1
+        s = np.sort(x[pos])
+        out = []
+        for need, side in ((need_hi, 'hi'), (need_lo, 'lo')):
+            j = rank_from_end(need)
+            if not rank_ok(j): out.append(None); continue
+            g = s[m - j] if side == 'hi' else s[j - 1]
+            beyond = (x >= g) if side == 'hi' else (x <= g)
+            eq = int(np.count_nonzero(x == g)); stored = int(np.count_nonzero(beyond)) - eq
+            out.append((stored <= cap and stored + eq >= need, stored, eq, need))
+        return out
+
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal(n, dtype=np.float32) * 2
+    well_behaved = {'randn': base, 'relu': np.maximum(base, 0), 'relu6-like': np.clip(base, 0, 1.5), 'student-t(2)': rng.standard_t(2, n).astype(np.float32)}
+    for name, x in well_behaved.items():
+        for q in (0.9999, 0.99999, 0.999):
+            for v in verdicts(x, q):
+                assert v is not None and v[0], (name, q, v)
+                assert v[1] <= 8 * max(v[3], 12 * stride), (name, q, v)                       # and not wastefully many: the finish walks them
+    # q = 0.99 on 8 Mi elements wants 84 K elements per tail: more than the buffer is allowed to hold on average -> no speculation at all
+    assert all(v is None for v in verdicts(base, 0.99))
+    lied = base.copy(); lied[pos[:64]] = 1e6; lied[pos[64:128]] = -1e6
+    for v in verdicts(lied, 0.9999): assert v is not None and not v[0] and v[1] + v[2] < v[3]   # too few candidates: the regular passes take over
+    flat = np.maximum(base, 0); flat[pos] = 3.0
+    hi, lo = verdicts(flat, 0.9999)
+    assert not hi[0] and hi[1] > cap and not lo[0]                                           # too many: overflow is detected, the buffer handed back
