@@ -73,14 +73,16 @@ def test_linear_quantize_backward_the_way_the_reference_tests_it(ppq):
     torch.manual_seed(1)
     policy = RoundingPolicy.ROUND_HALF_EVEN
 
-    def grads(value, dy, scale, offset, reduce_dims):
-        qt = ppq_tensor_round(value / scale, policy=policy) + offset
-        clipped = qt.clip(Q_MIN, Q_MAX)
-        dx = torch.where(clipped != qt, torch.zeros_like(dy), dy)
-        ds = torch.where(clipped == qt, (((qt - offset) * scale) - value) * dy / scale, torch.zeros_like(dy))
-        ds = ds + torch.where(qt > Q_MAX, (Q_MAX - offset) * dy, torch.zeros_like(dy)) + torch.where(qt < Q_MIN, (Q_MIN - offset) * dy, torch.zeros_like(dy))
-        ds = ds.sum() if reduce_dims is None else ds.transpose(0, reduce_dims).flatten(1).sum(dim=-1)
-        return dx, ds / sqrt(value.numel() * (Q_MAX - Q_MIN))                # the whole tensor's element count for per-channel too (test_cuda_kernel.py:118)
+    def grads(value, dy, scale, offset, axis):
+        """Straight-through gradient of fake-quant w.r.t. the input and LSQ-style gradient w.r.t. the scale, normalised by sqrt(numel * levels)."""
+        q = ppq_tensor_round(value / scale, policy=policy) + offset
+        below, above = q < Q_MIN, q > Q_MAX
+        inside = ~(below | above)
+        dx = dy * inside
+        per_elem = inside * (((q - offset) * scale - value) / scale) + above * (Q_MAX - offset) + below * (Q_MIN - offset)
+        ds = per_elem * dy
+        ds = ds.sum() if axis is None else ds.movedim(axis, 0).flatten(1).sum(dim=1)
+        return dx, ds / sqrt(value.numel() * (Q_MAX - Q_MIN))               # the whole tensor's element count, per channel too (test_cuda_kernel.py:118)
 
     def check_scale_grad(got, want, tag):
         snr = torch_snr_error(got.reshape([1, -1]), want.reshape([1, -1])).item()
