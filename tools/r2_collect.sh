@@ -9,7 +9,8 @@ for f in r2d_kbench.txt r2d_kbench_kl_old.txt r2d_vs_reference_kernels.md r2d_be
   [ -s gpurun_out/$f ] && cp gpurun_out/$f profiles/$(echo $f | sed 's/^r2[a-e]_/r02_/')
 done
 # the bench lines of the final build (call F: inputs through the device ring)
-for f in r2f_bench_n1.json r2f_bench_yolo_n1.json r2f_bench_e2e_1.json r2f_bench_e2e_2.json r2g_bench_n1.json r2g_bench_n2.json; do
+[ -s gpurun_out/r2f_bench_n1.json ] && cp gpurun_out/r2f_bench_n1.json profiles/r02_bench_n1_callF.json
+for f in r2f_bench_yolo_n1.json r2f_bench_e2e_1.json r2f_bench_e2e_2.json r2g_bench_n1.json r2g_bench_n2.json; do
   [ -s gpurun_out/$f ] && cp gpurun_out/$f profiles/$(echo $f | sed 's/^r2[a-g]_/r02_/')
 done
 [ -s gpurun_out/r2e_bench_e2e10.json ] && cp gpurun_out/r2e_bench_e2e10.json profiles/r02_before_ring_bench_e2e10.json
