@@ -51,114 +51,122 @@ def extension():
     return CUDA_COMPLIER.CUDA_EXTENSION
 
 
+def _dense(t: torch.Tensor) -> torch.Tensor:
+    """The reference wrappers make their operands contiguous before the call (ffi.py:199-306); same here."""
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ext():
+    return CUDA_COMPLIER.CUDA_EXTENSION
+
+
 class CUDA:
-    """Static wrappers with the reference's names and argument orders (ffi.py:56-350)."""
+    """Static wrappers with the reference's names and argument orders (ffi.py:56-350).  The only logic in them is what the reference's
+    wrappers do themselves: argument re-ordering between Python and C++, `contiguous()`, and the exponent check of the float formats."""
 
     @staticmethod
     def LinearQuantize_T(tensor: torch.Tensor, scales: torch.Tensor, offsets: torch.Tensor, minimum: int = -128,
                          maximum: int = 127, rounding: int = 0) -> torch.Tensor:
-        return CUDA_COMPLIER.CUDA_EXTENSION.QuantizeTensor_LT(tensor, scales, offsets, minimum, maximum, rounding)
+        return _ext().QuantizeTensor_LT(tensor, scales, offsets, minimum, maximum, rounding)
 
     @staticmethod
     def LinearQuantize_C(tensor: torch.Tensor, scales: torch.Tensor, offsets: torch.Tensor, channel_axis: int,
                          minimum: int = -128, maximum: int = 127, rounding: int = 0) -> torch.Tensor:
-        return CUDA_COMPLIER.CUDA_EXTENSION.QuantizeTensor_LC(tensor, scales, offsets, minimum, maximum, channel_axis, rounding)
+        return _ext().QuantizeTensor_LC(tensor, scales, offsets, minimum, maximum, channel_axis, rounding)
 
     @staticmethod
     def LinearQuantize_T_B(tensor, scales, offsets, dy, minimum: int, maximum: int, rounding: int) -> List[torch.Tensor]:
-        return CUDA_COMPLIER.CUDA_EXTENSION.QuantizeTensor_LT_B(tensor, scales, offsets, dy, minimum, maximum, rounding)
+        return _ext().QuantizeTensor_LT_B(tensor, scales, offsets, dy, minimum, maximum, rounding)
 
     @staticmethod
     def LinearQuantize_C_B(tensor, scales, offsets, dy, minimum: int, maximum: int, channel_axis: int,
                            rounding: int) -> List[torch.Tensor]:
-        return CUDA_COMPLIER.CUDA_EXTENSION.QuantizeTensor_LC_B(tensor, scales, offsets, dy, minimum, maximum, rounding, channel_axis)
+        return _ext().QuantizeTensor_LC_B(tensor, scales, offsets, dy, minimum, maximum, rounding, channel_axis)
 
     @staticmethod
     def Histogram_T(tensor: torch.Tensor, histogram: torch.Tensor, scale: float, clip_outliers: bool = True) -> torch.Tensor:
-        CUDA_COMPLIER.CUDA_EXTENSION.Histogram_T(tensor, scale, clip_outliers, histogram)
+        _ext().Histogram_T(tensor, scale, clip_outliers, histogram)
         return histogram
 
     @staticmethod
     def Histogram_Asymmetric_T(min_value: float, max_value: float, tensor: torch.Tensor, histogram: torch.Tensor,
                                clip_outliers: bool = True) -> torch.Tensor:
-        CUDA_COMPLIER.CUDA_EXTENSION.Histogram_Asymmetric_T(min_value, max_value, tensor, clip_outliers, histogram)
+        _ext().Histogram_Asymmetric_T(min_value, max_value, tensor, clip_outliers, histogram)
         return histogram
 
     @staticmethod
     def Histogram_C(tensor: torch.Tensor, channel_axis: int, histogram: torch.Tensor, scale: float,
                     clip_outliers: bool = True) -> torch.Tensor:
-        CUDA_COMPLIER.CUDA_EXTENSION.Histogram_C(tensor, channel_axis, scale, clip_outliers, histogram)
+        _ext().Histogram_C(tensor, channel_axis, scale, clip_outliers, histogram)
         return histogram
 
     @staticmethod
     def Quantile(tensor: torch.Tensor, q: float) -> torch.Tensor:
-        return CUDA_COMPLIER.CUDA_EXTENSION.Quantile_T(tensor, q)
+        return _ext().Quantile_T(tensor, q)
 
     @staticmethod
     def TensorClip_T(tensor: torch.Tensor, reference: torch.Tensor, limit: torch.Tensor) -> torch.Tensor:
-        if not tensor.is_contiguous(): tensor = tensor.contiguous()
-        if not reference.is_contiguous(): reference = reference.contiguous()
-        return CUDA_COMPLIER.CUDA_EXTENSION.TensorClip_T(tensor, reference, limit)
+        tensor = _dense(tensor)
+        reference = _dense(reference)
+        return _ext().TensorClip_T(tensor, reference, limit)
 
     @staticmethod
     def TensorClip_C(tensor: torch.Tensor, reference: torch.Tensor, limit: torch.Tensor, channel_axis: int) -> torch.Tensor:
-        if not tensor.is_contiguous(): tensor = tensor.contiguous()
-        if not reference.is_contiguous(): reference = reference.contiguous()
-        return CUDA_COMPLIER.CUDA_EXTENSION.TensorClip_C(tensor, reference, limit, channel_axis)
+        tensor = _dense(tensor)
+        reference = _dense(reference)
+        return _ext().TensorClip_C(tensor, reference, limit, channel_axis)
 
     @staticmethod
     def RoundingLoss_LT(tensor, scales, offsets, minimum: int = -128, maximum: int = 127, rounding: int = 0) -> torch.Tensor:
-        if not tensor.is_contiguous(): tensor = tensor.contiguous()
-        return CUDA_COMPLIER.CUDA_EXTENSION.RoundingLoss_LT(tensor, scales, offsets, minimum, maximum, rounding)
+        tensor = _dense(tensor)
+        return _ext().RoundingLoss_LT(tensor, scales, offsets, minimum, maximum, rounding)
 
     @staticmethod
     def RoundingLoss_LT_B(tensor, dy, scales, offsets, minimum: int = -128, maximum: int = 127, rounding: int = 0) -> torch.Tensor:
-        if not tensor.is_contiguous(): tensor = tensor.contiguous()
-        return CUDA_COMPLIER.CUDA_EXTENSION.RoundingLoss_LT_B(tensor, dy, scales, offsets, minimum, maximum, rounding)
+        tensor = _dense(tensor)
+        return _ext().RoundingLoss_LT_B(tensor, dy, scales, offsets, minimum, maximum, rounding)
 
     @staticmethod
     def RoundingLoss_LC(tensor, scales, offsets, channel_axis: int, minimum: int = -128, maximum: int = 127,
                         rounding: int = 0) -> torch.Tensor:
-        if not tensor.is_contiguous(): tensor = tensor.contiguous()
-        return CUDA_COMPLIER.CUDA_EXTENSION.RoundingLoss_LC(tensor, scales, offsets, minimum, maximum, channel_axis, rounding)
+        tensor = _dense(tensor)
+        return _ext().RoundingLoss_LC(tensor, scales, offsets, minimum, maximum, channel_axis, rounding)
 
     @staticmethod
     def RoundingLoss_LC_B(tensor, dy, scales, offsets, channel_axis: int, minimum: int = -128, maximum: int = 127,
                           rounding: int = 0) -> torch.Tensor:
-        if not tensor.is_contiguous(): tensor = tensor.contiguous()
-        return CUDA_COMPLIER.CUDA_EXTENSION.RoundingLoss_LC_B(tensor, dy, scales, offsets, minimum, maximum, channel_axis, rounding)
+        tensor = _dense(tensor)
+        return _ext().RoundingLoss_LC_B(tensor, dy, scales, offsets, minimum, maximum, channel_axis, rounding)
 
     @staticmethod
     def compute_mse_loss(histogram: list, start: int, step: int, end: int) -> float:
-        return CUDA_COMPLIER.CUDA_EXTENSION.compute_mse_loss(histogram, start, step, end)
+        return _ext().compute_mse_loss(histogram, start, step, end)
 
     @staticmethod
     def FloatingQuantize_T(tensor, scales, offsets, exponent: int = 4, mantissa: int = 3, minimum: float = -448,
                            maximum: float = +448, rounding: int = 0) -> torch.Tensor:
         if exponent <= 0: raise ValueError('Floating Quantization requires exponent > 0')
-        if not tensor.is_contiguous(): tensor = tensor.contiguous()
-        return CUDA_COMPLIER.CUDA_EXTENSION.QuantizeTensor_FT(tensor, scales, offsets, exponent, mantissa, minimum, maximum, rounding)
+        tensor = _dense(tensor)
+        return _ext().QuantizeTensor_FT(tensor, scales, offsets, exponent, mantissa, minimum, maximum, rounding)
 
     @staticmethod
     def FloatingQuantize_C(tensor, scales, offsets, channel_axis: int, exponent: int = 4, mantissa: int = 3,
                            minimum: float = -448, maximum: float = +448, rounding: int = 0) -> torch.Tensor:
         if exponent <= 0: raise ValueError('Floating Quantization requires exponent > 0')
-        if not tensor.is_contiguous(): tensor = tensor.contiguous()
-        return CUDA_COMPLIER.CUDA_EXTENSION.QuantizeTensor_FC(tensor, scales, offsets, exponent, mantissa, minimum, maximum,
-                                                              channel_axis, rounding)
+        tensor = _dense(tensor)
+        return _ext().QuantizeTensor_FC(tensor, scales, offsets, exponent, mantissa, minimum, maximum, channel_axis, rounding)
 
     @staticmethod
     def FloatingQuantize_T_B(tensor, scales, offsets, dy, exponent: int, mantissa: int, minimum: float, maximum: float,
                              rounding: int) -> List[torch.Tensor]:
-        if not tensor.is_contiguous(): tensor = tensor.contiguous()
-        return CUDA_COMPLIER.CUDA_EXTENSION.QuantizeTensor_FT_B(tensor, scales, offsets, dy, exponent, mantissa, minimum, maximum, rounding)
+        tensor = _dense(tensor)
+        return _ext().QuantizeTensor_FT_B(tensor, scales, offsets, dy, exponent, mantissa, minimum, maximum, rounding)
 
     @staticmethod
     def FloatingQuantize_C_B(tensor, scales, offsets, dy, exponent: int, mantissa: int, minimum: float, maximum: float,
                              channel_axis: int, rounding: int) -> List[torch.Tensor]:
-        if not tensor.is_contiguous(): tensor = tensor.contiguous()
-        return CUDA_COMPLIER.CUDA_EXTENSION.QuantizeTensor_FC_B(tensor, scales, offsets, dy, exponent, mantissa, minimum, maximum,
-                                                                rounding, channel_axis)
+        tensor = _dense(tensor)
+        return _ext().QuantizeTensor_FC_B(tensor, scales, offsets, dy, exponent, mantissa, minimum, maximum, rounding, channel_axis)
 
     @staticmethod
     def Sync():
@@ -169,14 +177,14 @@ class CUDA:
     def LinearQuantize_toInt(tensor, scales, offsets, channel_axis=None, minimum: int = -128, maximum: int = 127,
                              rounding: int = 0, out_bits: int = 8) -> torch.Tensor:
         axis = -1000 if channel_axis is None else channel_axis
-        return CUDA_COMPLIER.CUDA_EXTENSION.QuantizeTensor_toInt(tensor, scales, offsets, minimum, maximum, axis, rounding, out_bits)
+        return _ext().QuantizeTensor_toInt(tensor, scales, offsets, minimum, maximum, axis, rounding, out_bits)
 
     @staticmethod
     def MinMax_T(tensor: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
-        CUDA_COMPLIER.CUDA_EXTENSION.MinMax_T(tensor, minmax)
+        _ext().MinMax_T(tensor, minmax)
         return minmax
 
     @staticmethod
     def MinMax_C(tensor: torch.Tensor, channel_axis: int, mins: torch.Tensor, maxs: torch.Tensor):
-        CUDA_COMPLIER.CUDA_EXTENSION.MinMax_C(tensor, channel_axis, mins, maxs)
+        _ext().MinMax_C(tensor, channel_axis, mins, maxs)
         return mins, maxs
